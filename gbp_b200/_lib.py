@@ -1,0 +1,113 @@
+"""ctypes binding of libgbp_b200.so (include/gbp_b200.h).
+
+There is NO CPU implementation behind this module: if the CUDA library is missing, or no
+CUDA device is visible when a graph is created, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+
+ABI_VERSION = 1
+
+# gbp_field
+(F_CAM_BELIEF, F_LMK_BELIEF, F_CAM_PRIOR, F_LMK_PRIOR, F_MSG_CAM, F_MSG_LMK, F_LINPOINT, F_ITERS,
+ F_FLAGS, F_ADAPTIVE_VAR, F_MEASUREMENT, F_JACOBIAN_B, F_ADJ, F_FILE_INDEX, F_CAM_PARTIAL) = range(15)
+
+# stages
+ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING = 1, 2, 4, 8, 16
+
+LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
+
+# field -> (index kind, dtype, row width)
+FIELD_SHAPES = {
+    F_CAM_BELIEF: ("C", np.float64, 33), F_LMK_BELIEF: ("L", np.float64, 12),
+    F_CAM_PRIOR: ("C", np.float64, 27), F_LMK_PRIOR: ("L", np.float64, 9),
+    F_MSG_CAM: ("F", np.float64, 27), F_MSG_LMK: ("F", np.float64, 9),
+    F_LINPOINT: ("F", np.float64, 9), F_ITERS: ("F", np.int32, 1), F_FLAGS: ("F", np.int32, 1),
+    F_ADAPTIVE_VAR: ("F", np.float64, 1), F_MEASUREMENT: ("F", np.float64, 2),
+    F_JACOBIAN_B: ("F", np.float64, 20), F_ADJ: ("F", np.int32, 2), F_FILE_INDEX: ("F", np.int32, 1),
+    F_CAM_PARTIAL: ("C", np.float64, 27),
+}
+
+
+class GbpError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (message from gbp_last_error)."""
+
+    def __init__(self, status, message):
+        super().__init__(f"libgbp_b200 status {status}: {message}")
+        self.status = status
+
+
+class GbpConfig(C.Structure):
+    _fields_ = [("gauss_noise_std", C.c_double), ("eta_damping", C.c_double), ("beta", C.c_double),
+                ("Nstds", C.c_double), ("num_undamped_iters", C.c_int32), ("min_linear_iters", C.c_int32),
+                ("loss", C.c_int32), ("tile_edges", C.c_int32), ("lmk_block", C.c_int32), ("reserved", C.c_int32)]
+
+
+EXPORTS = [
+    "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_sizes",
+    "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
+    "gbp_ba_sweep_local", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
+    "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
+    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found.  gbp_b200 has no CPU fallback: build the CUDA library with "
+            f"`python -m gbp_b200.build` (needs nvcc) before using the BA engine.")
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.gbp_last_error.restype = C.c_char_p
+    lib.gbp_abi_version.restype = C.c_int
+    lib.gbp_device_count.restype = C.c_int
+    lib.gbp_ba_create.argtypes = [C.POINTER(GbpConfig), C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, vp,
+                                  C.c_int, vp, C.POINTER(vp)]
+    lib.gbp_ba_destroy.argtypes = [vp]
+    lib.gbp_ba_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.gbp_ba_prior_scan.argtypes = [vp, vp]
+    lib.gbp_ba_generate_priors.argtypes = [vp, C.c_double, vp]
+    lib.gbp_ba_set_priors.argtypes = [vp, vp, vp]
+    lib.gbp_ba_scale_priors.argtypes = [vp, C.c_double]
+    lib.gbp_ba_sweep_local.argtypes = [vp, C.c_int]
+    lib.gbp_ba_cam_update.argtypes = [vp, vp, C.c_int]
+    lib.gbp_ba_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.gbp_ba_update_beliefs.argtypes = [vp]
+    lib.gbp_ba_metrics.argtypes = [vp, dp]
+    lib.gbp_ba_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    lib.gbp_ba_write.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    lib.gbp_ba_fill_iters.argtypes = [vp, C.c_int32]
+    lib.gbp_ba_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.gbp_ba_set_params.argtypes = [vp, C.c_double, C.c_double, C.c_int32, C.c_int32]
+    lib.gbp_ba_synchronize.argtypes = [vp]
+    lib.gbp_ba_time_iterations.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]
+    lib.gbp_ba_launch_count.argtypes = [vp]
+    lib.gbp_ba_launch_count.restype = C.c_int64
+    lib.gbp_reprojection_eval.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp]
+    if lib.gbp_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libgbp_b200 ABI {lib.gbp_abi_version()} != binding {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise GbpError(status, load().gbp_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None

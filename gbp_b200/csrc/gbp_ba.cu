@@ -1,0 +1,751 @@
+// gbp_ba.cu -- handle, host-side graph compiler and the C ABI of libgbp_b200.so.
+// See include/gbp_b200.h for the contract and the reference methods each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gbp_b200.h"
+#include "gbp_kernels.cuh"
+
+using namespace gbp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(GBP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define CHECK_H(h)                                             \
+    if (!(h)) return fail(GBP_ERR_INVALID, "null gbp_handle"); \
+    CU(cudaSetDevice((h)->device))
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct gbp_ba_graph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    gbp_config cfg{};
+    Intrinsics K{};
+    int C = 0, L = 0;
+    long long F = 0;
+    int T = 32;        // edges per tile
+    int n_tiles = 0;
+    long long n_slots = 0;
+    bool robust = false;
+    bool priors_set = false;
+    long long launches = 0;
+
+    // host copies (factor order)
+    std::vector<int> h_slot_of_factor, h_file_of_factor, h_adj;
+
+    // device state
+    DevBuf<Tile> tiles;
+    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
+    DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
+    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial;
+    DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
+
+    std::map<int, cudaGraphExec_t> graphs;  // key: stages
+
+    ~gbp_ba_graph() {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        tiles.release(); lmk_idx.release(); iters.release(); flags.release(); slot_of_factor.release();
+        lmk_ptr.release(); lmk_slots.release(); cam_tile_ptr.release(); cam_tiles.release();
+        z.release(); linpoint.release(); msg_cam.release(); msg_lmk.release(); sigma2a.release();
+        cam_belief.release(); lmk_belief.release(); cam_prior.release(); lmk_prior.release(); cam_partial.release();
+        tile_partial.release(); tile_metric.release(); metric_out.release(); edge_max.release();
+        tile_max.release(); cam_max.release();
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+SweepParams sweep_params(gbp_ba_graph* g, int stages) {
+    SweepParams p{};
+    p.tiles = g->tiles.p; p.lmk_idx = g->lmk_idx.p; p.z = g->z.p; p.linpoint = g->linpoint.p;
+    p.msg_cam = g->msg_cam.p; p.msg_lmk = g->msg_lmk.p; p.iters = g->iters.p; p.flags = g->flags.p;
+    p.sigma2a = g->sigma2a.p; p.cam_belief = g->cam_belief.p; p.lmk_belief = g->lmk_belief.p;
+    p.tile_partial = g->tile_partial.p; p.K = g->K;
+    p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std;
+    p.eta_damping = g->cfg.eta_damping; p.beta = g->cfg.beta; p.nstds = g->cfg.Nstds;
+    p.num_undamped = g->cfg.num_undamped_iters; p.min_linear = g->cfg.min_linear_iters;
+    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles;
+    return p;
+}
+
+template <int T>
+int launch_sweep_t(gbp_ba_graph* g, int stages) {
+    const SweepParams p = sweep_params(g, stages);
+    constexpr size_t smem = sweep_smem_bytes<T>();
+    static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
+    if (g->robust)
+        sweep_kernel<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
+    else
+        sweep_kernel<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    g->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+int launch_sweep(gbp_ba_graph* g, int stages) {
+    if (g->n_tiles == 0) return GBP_OK;
+    switch (g->T) {
+        case 32: return launch_sweep_t<32>(g, stages);
+        case 64: return launch_sweep_t<64>(g, stages);
+        default: return launch_sweep_t<128>(g, stages);
+    }
+}
+
+// landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise)
+int launch_belief(gbp_ba_graph* g, int finalise) {
+    BeliefParams p{};
+    p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
+    p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
+    p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
+    p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p;
+    p.L = g->L; p.C = g->C; p.lmk_blocks = (g->L + 127) / 128; p.finalise = finalise;
+    const int blocks = p.lmk_blocks + (g->C + 3) / 4;
+    if (blocks == 0) return GBP_OK;
+    belief_kernel<<<blocks, 128, 0, g->stream>>>(p);
+    g->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+template <int T>
+int launch_metric_t(gbp_ba_graph* g) {
+    MetricParams p{};
+    p.tiles = g->tiles.p; p.lmk_idx = g->lmk_idx.p; p.z = g->z.p; p.iters = g->iters.p; p.sigma2a = g->sigma2a.p;
+    p.cam_belief = g->cam_belief.p; p.lmk_belief = g->lmk_belief.p; p.tile_metric = g->tile_metric.p; p.K = g->K;
+    p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std; p.robust = g->robust ? 1 : 0;
+    metric_kernel<T><<<g->n_tiles, T, 0, g->stream>>>(p);
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+template <int T>
+int launch_lammax_t(gbp_ba_graph* g) {
+    edge_lammax_kernel<T><<<g->n_tiles, T, 0, g->stream>>>(g->tiles.p, g->linpoint.p, g->sigma2a.p, g->robust ? 1 : 0,
+                                                           g->cfg.gauss_noise_std * g->cfg.gauss_noise_std, g->K,
+                                                           g->edge_max.p, g->tile_max.p);
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+template <int T>
+int launch_init_t(gbp_ba_graph* g) {
+    init_edges_kernel<T><<<g->n_tiles, T, 0, g->stream>>>(g->tiles.p, g->lmk_idx.p, g->cam_belief.p, g->lmk_belief.p,
+                                                          g->cfg.gauss_noise_std * g->cfg.gauss_noise_std, g->linpoint.p,
+                                                          g->iters.p, g->flags.p, g->sigma2a.p);
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+#define DISPATCH_T(g, fn)                         \
+    ((g)->T == 32 ? fn<32>(g) : (g)->T == 64 ? fn<64>(g) : fn<128>(g))
+
+struct FieldInfo {
+    int indexed;   // 0 = keyframes, 1 = landmarks, 2 = factors
+    int words;     // row width in 4-byte words
+    bool writable;
+};
+
+bool field_info(int field, FieldInfo* fi) {
+    switch (field) {
+        case GBP_F_CAM_BELIEF: *fi = {0, CAM_B * 2, true}; return true;
+        case GBP_F_LMK_BELIEF: *fi = {1, LMK_B * 2, true}; return true;
+        case GBP_F_CAM_PRIOR: *fi = {0, CAM_M * 2, true}; return true;
+        case GBP_F_LMK_PRIOR: *fi = {1, LMK_M * 2, true}; return true;
+        case GBP_F_MSG_CAM: *fi = {2, CAM_M * 2, true}; return true;
+        case GBP_F_MSG_LMK: *fi = {2, LMK_M * 2, true}; return true;
+        case GBP_F_LINPOINT: *fi = {2, 18, true}; return true;
+        case GBP_F_ITERS_SINCE_RELIN: *fi = {2, 1, true}; return true;
+        case GBP_F_FLAGS: *fi = {2, 1, true}; return true;
+        case GBP_F_ADAPTIVE_VAR: *fi = {2, 2, true}; return true;
+        case GBP_F_MEASUREMENT: *fi = {2, 4, false}; return true;
+        case GBP_F_JACOBIAN_B: *fi = {2, 40, false}; return true;
+        case GBP_F_ADJ: *fi = {2, 2, false}; return true;
+        case GBP_F_FILE_INDEX: *fi = {2, 1, false}; return true;
+        case GBP_F_CAM_PARTIAL: *fi = {0, CAM_M * 2, false}; return true;
+        default: return false;
+    }
+}
+
+void* field_dev_ptr(gbp_ba_graph* g, int field) {
+    switch (field) {
+        case GBP_F_CAM_BELIEF: return g->cam_belief.p;
+        case GBP_F_LMK_BELIEF: return g->lmk_belief.p;
+        case GBP_F_CAM_PRIOR: return g->cam_prior.p;
+        case GBP_F_LMK_PRIOR: return g->lmk_prior.p;
+        case GBP_F_MSG_CAM: return g->msg_cam.p;
+        case GBP_F_MSG_LMK: return g->msg_lmk.p;
+        case GBP_F_LINPOINT: return g->linpoint.p;
+        case GBP_F_ITERS_SINCE_RELIN: return g->iters.p;
+        case GBP_F_FLAGS: return g->flags.p;
+        case GBP_F_ADAPTIVE_VAR: return g->sigma2a.p;
+        case GBP_F_MEASUREMENT: return g->z.p;
+        case GBP_F_CAM_PARTIAL: return g->cam_partial.p;
+        default: return nullptr;
+    }
+}
+
+int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out) {
+    auto it = g->graphs.find(stages);
+    if (it != g->graphs.end()) { *out = it->second; return GBP_OK; }
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = g->launches;
+    int rc = launch_sweep(g, stages);
+    if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1);
+    g->launches = before;  // capture does not execute
+    cudaError_t e = cudaStreamEndCapture(g->stream, &graph);
+    if (rc != GBP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    g->graphs[stages] = exec;
+    *out = exec;
+    return GBP_OK;
+}
+
+int iteration_stages(int robustify, int local_relin) {
+    // synchronous_iteration (gbp/gbp.py:86-92) for a graph with nonlinear factors
+    int st = ST_MESSAGES | ST_BELIEFS;
+    if (robustify) st |= ST_ROBUSTIFY;
+    if (local_relin) st |= ST_RELIN | ST_LOCAL_DAMPING;
+    return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gbp_last_error(void) { return g_err.c_str(); }
+int gbp_abi_version(void) { return GBP_B200_ABI_VERSION; }
+
+int gbp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id,
+                  const double* z, const double* cam_mu0, const double* lmk_mu0, const double K[4], int device,
+                  void* stream, gbp_handle* out) {
+    if (!cfg || !out || !K) return fail(GBP_ERR_INVALID, "null argument");
+    if (C < 0 || L < 0 || F < 0) return fail(GBP_ERR_INVALID, "negative size");
+    if (F > 0 && (!cam_id || !lmk_id || !z)) return fail(GBP_ERR_INVALID, "null measurement arrays");
+    if ((C > 0 && !cam_mu0) || (L > 0 && !lmk_mu0)) return fail(GBP_ERR_INVALID, "null initial means");
+    if (cfg->loss < 0 || cfg->loss > 2) return fail(GBP_ERR_INVALID, "unknown loss %d", cfg->loss);
+    if (!(cfg->gauss_noise_std > 0)) return fail(GBP_ERR_INVALID, "gauss_noise_std must be > 0");
+    *out = nullptr;
+    if (gbp_device_count() <= 0)
+        return fail(GBP_ERR_NO_DEVICE, "no CUDA device visible: gbp_b200 has no CPU fallback for the BA sweep");
+    if (device < 0 || device >= gbp_device_count()) return fail(GBP_ERR_INVALID, "device %d out of range", device);
+    for (int64_t f = 0; f < F; ++f) {
+        if (cam_id[f] < 0 || cam_id[f] >= C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)f, cam_id[f]);
+        if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
+    }
+    CU(cudaSetDevice(device));
+    gbp_ba_graph* g = new (std::nothrow) gbp_ba_graph();
+    if (!g) return fail(GBP_ERR_INVALID, "out of host memory");
+    g->device = device;
+    g->cfg = *cfg;
+    g->K = Intrinsics{K[0], K[1], K[2], K[3]};
+    g->C = C; g->L = L; g->F = F;
+    g->robust = cfg->loss != GBP_LOSS_NONE;
+    if (stream) {
+        g->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete g; return fail(GBP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        g->own_stream = true;
+    }
+
+    // ---------------- host graph compiler ----------------
+    int T = cfg->tile_edges;
+    if (T == 0) T = F >= 128LL * 148 * 4 ? 128 : (F >= 64LL * 148 * 2 ? 64 : 32);
+    if (T != 32 && T != 64 && T != 128) { delete g; return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
+    g->T = T;
+    long long lblock = cfg->lmk_block;
+    if (lblock <= 0) lblock = ((long long)L * LMK_B * 8 <= (24LL << 20)) ? std::max(L, 1) : 262144;
+    const long long nb = L > 0 ? (L + lblock - 1) / lblock : 1;
+
+    // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130)
+    std::vector<long long> cam_start((size_t)C + 1, 0);
+    for (int64_t i = 0; i < F; ++i) cam_start[cam_id[i] + 1]++;
+    for (int c = 0; c < C; ++c) cam_start[c + 1] += cam_start[c];
+    g->h_file_of_factor.assign((size_t)F, 0);
+    {
+        std::vector<long long> pos(cam_start.begin(), cam_start.end() - 1);
+        for (int64_t i = 0; i < F; ++i) g->h_file_of_factor[(size_t)pos[cam_id[i]]++] = (int)i;
+    }
+    g->h_adj.assign((size_t)F * 2, 0);
+    for (int64_t f = 0; f < F; ++f) {
+        const int i = g->h_file_of_factor[(size_t)f];
+        g->h_adj[2 * f] = cam_id[i];
+        g->h_adj[2 * f + 1] = lmk_id[i];
+    }
+    // storage order: (landmark block, camera) runs, factor order inside a run
+    const size_t nkeys = (size_t)nb * (size_t)std::max(C, 1);
+    std::vector<long long> run_start(nkeys + 1, 0);
+    auto key_of = [&](int64_t f) { return (size_t)(g->h_adj[2 * f + 1] / lblock) * (size_t)C + (size_t)g->h_adj[2 * f]; };
+    for (int64_t f = 0; f < F; ++f) run_start[key_of(f) + 1]++;
+    // tiles per run
+    std::vector<Tile> tiles;
+    std::vector<long long> run_slot(nkeys, 0);
+    {
+        long long tcount = 0;
+        for (size_t k = 0; k < nkeys; ++k) {
+            const long long cnt = run_start[k + 1];
+            run_slot[k] = tcount * T;
+            long long left = cnt;
+            while (left > 0) {
+                Tile t;
+                t.cam = (int)(k % (size_t)std::max(C, 1));
+                t.count = (int)std::min<long long>(left, T);
+                tiles.push_back(t);
+                left -= t.count;
+                ++tcount;
+            }
+        }
+    }
+    g->n_tiles = (int)tiles.size();
+    g->n_slots = (long long)tiles.size() * T;
+    if (g->n_slots >= (1LL << 31)) { delete g; return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
+    g->h_slot_of_factor.assign((size_t)F, 0);
+    {
+        std::vector<long long> pos(run_slot);
+        for (int64_t f = 0; f < F; ++f) g->h_slot_of_factor[(size_t)f] = (int)pos[key_of(f)]++;
+        // runs are contiguous in slots except for the padding of their last tile, which lies at
+        // the END of the run, so consecutive positions are correct.
+    }
+    // slot-ordered inputs
+    std::vector<int> h_lmk_idx((size_t)g->n_slots, 0);
+    std::vector<double> h_z((size_t)g->n_slots * 2, 0.0);
+    for (int64_t f = 0; f < F; ++f) {
+        const size_t s = (size_t)g->h_slot_of_factor[(size_t)f];
+        const int i = g->h_file_of_factor[(size_t)f];
+        h_lmk_idx[s] = g->h_adj[2 * f + 1];
+        h_z[2 * s] = z[2 * (size_t)i];
+        h_z[2 * s + 1] = z[2 * (size_t)i + 1];
+    }
+    // CSR by landmark over slots (factor order inside a landmark = adj_factors order)
+    std::vector<int> h_lmk_ptr((size_t)L + 1, 0), h_lmk_slots((size_t)F, 0);
+    for (int64_t f = 0; f < F; ++f) h_lmk_ptr[(size_t)g->h_adj[2 * f + 1] + 1]++;
+    for (int l = 0; l < L; ++l) h_lmk_ptr[l + 1] += h_lmk_ptr[l];
+    {
+        std::vector<int> pos(h_lmk_ptr.begin(), h_lmk_ptr.end() - 1);
+        for (int64_t f = 0; f < F; ++f) h_lmk_slots[(size_t)pos[g->h_adj[2 * f + 1]]++] = g->h_slot_of_factor[(size_t)f];
+    }
+    // CSR by camera over tiles
+    std::vector<int> h_cam_tile_ptr((size_t)C + 1, 0), h_cam_tiles(tiles.size(), 0);
+    for (const Tile& t : tiles) h_cam_tile_ptr[(size_t)t.cam + 1]++;
+    for (int c = 0; c < C; ++c) h_cam_tile_ptr[c + 1] += h_cam_tile_ptr[c];
+    {
+        std::vector<int> pos(h_cam_tile_ptr.begin(), h_cam_tile_ptr.end() - 1);
+        for (size_t t = 0; t < tiles.size(); ++t) h_cam_tiles[(size_t)pos[tiles[t].cam]++] = (int)t;
+    }
+
+    // ---------------- device allocation + upload ----------------
+    auto bail = [&](cudaError_t e, const char* what) {
+        delete g;
+        return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+#define ALLOC(buf, n) if ((e = g->buf.alloc(n)) != cudaSuccess) return bail(e, "cudaMalloc " #buf)
+    const size_t S = (size_t)g->n_slots;
+    ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
+    ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
+    ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
+    ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * CAM_M); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
+    ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
+    ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
+    ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3); ALLOC(metric_out, 4);
+    ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+#undef ALLOC
+#define UP(buf, vec) if (!(vec).empty() && (e = cudaMemcpyAsync(g->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload " #buf)
+    UP(tiles, tiles); UP(lmk_idx, h_lmk_idx); UP(z, h_z); UP(slot_of_factor, g->h_slot_of_factor);
+    UP(lmk_ptr, h_lmk_ptr); UP(lmk_slots, h_lmk_slots); UP(cam_tile_ptr, h_cam_tile_ptr); UP(cam_tiles, h_cam_tiles);
+#undef UP
+#define ZERO(buf) if ((e = cudaMemsetAsync(g->buf.p, 0, std::max<size_t>(g->buf.bytes(), 1), g->stream)) != cudaSuccess) return bail(e, "memset " #buf)
+    ZERO(msg_cam); ZERO(msg_lmk); ZERO(cam_prior); ZERO(lmk_prior); ZERO(cam_partial); ZERO(tile_partial);
+    ZERO(edge_max); ZERO(tile_max); ZERO(cam_max);
+#undef ZERO
+    // beliefs: eta = Lambda = 0, mu = initial means; edges linearised at those means
+    {
+        DevBuf<double> tmp;
+        const size_t nmu = std::max((size_t)C * 6, (size_t)L * 3);
+        if ((e = tmp.alloc(nmu)) != cudaSuccess) return bail(e, "cudaMalloc staging");
+        if (C > 0) {
+            cudaMemcpyAsync(tmp.p, cam_mu0, (size_t)C * 6 * 8, cudaMemcpyHostToDevice, g->stream);
+            init_belief_kernel<<<(C + 127) / 128, 128, 0, g->stream>>>(tmp.p, C, 6, CAM_B, g->cam_belief.p);
+            cudaStreamSynchronize(g->stream);
+        }
+        if (L > 0) {
+            cudaMemcpyAsync(tmp.p, lmk_mu0, (size_t)L * 3 * 8, cudaMemcpyHostToDevice, g->stream);
+            init_belief_kernel<<<(L + 127) / 128, 128, 0, g->stream>>>(tmp.p, L, 3, LMK_B, g->lmk_belief.p);
+            cudaStreamSynchronize(g->stream);
+        }
+        tmp.release();
+    }
+    if (g->n_tiles > 0) {
+        int rc = DISPATCH_T(g, launch_init_t);
+        if (rc != GBP_OK) { delete g; return rc; }
+    }
+    if ((e = cudaStreamSynchronize(g->stream)) != cudaSuccess) return bail(e, "graph initialisation");
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "graph initialisation kernels");
+    *out = g;
+    return GBP_OK;
+}
+
+int gbp_ba_destroy(gbp_handle h) {
+    if (!h) return GBP_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    delete h;
+    return GBP_OK;
+}
+
+int gbp_ba_sizes(gbp_handle h, int64_t out[6]) {
+    if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
+    out[0] = h->C; out[1] = h->L; out[2] = h->F; out[3] = h->n_tiles; out[4] = h->T; out[5] = h->n_slots;
+    return GBP_OK;
+}
+
+int gbp_ba_prior_scan(gbp_handle h, double* cam_max) {
+    CHECK_H(h);
+    if (h->n_tiles > 0) {
+        int rc = DISPATCH_T(h, launch_lammax_t);
+        if (rc != GBP_OK) return rc;
+    }
+    if (h->C > 0) {
+        cam_max_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->tile_max.p, h->cam_tile_ptr.p, h->cam_tiles.p, h->C, h->cam_max.p);
+        CU(cudaGetLastError());
+        if (cam_max) CU(cudaMemcpyAsync(cam_max, h->cam_max.p, (size_t)h->C * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return GBP_OK;
+}
+
+int gbp_ba_generate_priors(gbp_handle h, double weaker_factor, const double* cam_max) {
+    CHECK_H(h);
+    if (!(weaker_factor > 0)) return fail(GBP_ERR_INVALID, "weaker_factor must be > 0");
+    if (cam_max) {
+        // caller already ran gbp_ba_prior_scan on every rank and reduced the maxima
+        if (h->C > 0) CU(cudaMemcpyAsync(h->cam_max.p, cam_max, (size_t)h->C * 8, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        int rc = gbp_ba_prior_scan(h, nullptr);
+        if (rc != GBP_OK) return rc;
+    }
+    if (h->C > 0) cam_prior_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_max.p, weaker_factor, h->C, h->cam_belief.p, h->cam_prior.p);
+    if (h->L > 0) lmk_prior_kernel<<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->edge_max.p, h->lmk_ptr.p, h->lmk_slots.p, weaker_factor, h->L, h->lmk_belief.p, h->lmk_prior.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    h->priors_set = true;
+    return GBP_OK;
+}
+
+int gbp_ba_set_priors(gbp_handle h, const double* cam_lam, const double* lmk_lam) {
+    CHECK_H(h);
+    if ((h->C > 0 && !cam_lam) || (h->L > 0 && !lmk_lam)) return fail(GBP_ERR_INVALID, "null prior precision");
+    if (h->C > 0) {
+        CU(cudaMemcpy2DAsync(h->cam_prior.p + 6, CAM_M * 8, cam_lam, 21 * 8, 21 * 8, h->C, cudaMemcpyHostToDevice, h->stream));
+        prior_eta_kernel<6><<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->C, h->cam_belief.p, CAM_B, 27, h->cam_prior.p);
+    }
+    if (h->L > 0) {
+        CU(cudaMemcpy2DAsync(h->lmk_prior.p + 3, LMK_M * 8, lmk_lam, 6 * 8, 6 * 8, h->L, cudaMemcpyHostToDevice, h->stream));
+        prior_eta_kernel<3><<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->L, h->lmk_belief.p, LMK_B, 9, h->lmk_prior.p);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    h->priors_set = true;
+    return GBP_OK;
+}
+
+int gbp_ba_scale_priors(gbp_handle h, double factor) {
+    CHECK_H(h);
+    const long long nc = (long long)h->C * CAM_M, nl = (long long)h->L * LMK_M;
+    if (nc > 0) scale_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(h->cam_prior.p, nc, factor);
+    if (nl > 0) scale_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, h->stream>>>(h->lmk_prior.p, nl, factor);
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+int gbp_ba_sweep_local(gbp_handle h, int stages) {
+    CHECK_H(h);
+    if (stages & (ST_ROBUSTIFY | ST_RELIN | ST_MESSAGES | ST_BELIEFS)) {
+        // the sweep kernel also produces the per-tile keyframe sums when beliefs are requested
+        int rc = launch_sweep(h, stages);
+        if (rc != GBP_OK) return rc;
+    }
+    if (stages & ST_BELIEFS) return launch_belief(h, 0);
+    return GBP_OK;
+}
+
+int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {
+    CHECK_H(h);
+    if (h->C == 0) return GBP_OK;
+    const double* src = partials_dev ? partials_dev : h->cam_partial.p;
+    if (!partials_dev) nranks = 1;
+    if (nranks < 1) return fail(GBP_ERR_INVALID, "nranks must be >= 1");
+    cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p);
+    h->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
+    CHECK_H(h);
+    if (n_iters < 0) return fail(GBP_ERR_INVALID, "n_iters < 0");
+    if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
+    const int st = iteration_stages(robustify, local_relin);
+    cudaGraphExec_t exec;
+    int rc = get_graph(h, st, &exec);
+    if (rc != GBP_OK) return rc;
+    const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
+    for (int i = 0; i < n_iters; ++i) CU(cudaGraphLaunch(exec, h->stream));
+    h->launches += (long long)per_iter * n_iters;
+    return GBP_OK;
+}
+
+int gbp_ba_update_beliefs(gbp_handle h) {
+    CHECK_H(h);
+    int rc = launch_sweep(h, ST_BELIEFS);  // only the per-tile sums of the stored messages
+    if (rc != GBP_OK) return rc;
+    return launch_belief(h, 1);
+}
+
+int gbp_ba_metrics(gbp_handle h, double out[3]) {
+    CHECK_H(h);
+    if (!out) return fail(GBP_ERR_INVALID, "null out");
+    out[0] = out[1] = out[2] = 0.0;
+    if (h->n_tiles == 0) return GBP_OK;
+    int rc = DISPATCH_T(h, launch_metric_t);
+    if (rc != GBP_OK) return rc;
+    reduce_rows_kernel<3><<<1, 256, 0, h->stream>>>(h->tile_metric.p, h->n_tiles, h->metric_out.p);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, h->metric_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GBP_OK;
+}
+
+int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes) {
+    CHECK_H(h);
+    FieldInfo fi;
+    if (!field_info(field, &fi)) return fail(GBP_ERR_INVALID, "unknown field %d", field);
+    const long long rows = fi.indexed == 0 ? h->C : fi.indexed == 1 ? h->L : h->F;
+    const size_t need = (size_t)rows * fi.words * 4;
+    if (bytes != need) return fail(GBP_ERR_INVALID, "field %d: expected %zu bytes, got %zu", field, need, bytes);
+    if (need == 0) return GBP_OK;
+    if (!host_dst) return fail(GBP_ERR_INVALID, "null destination");
+    if (field == GBP_F_ADJ) { memcpy(host_dst, h->h_adj.data(), need); return GBP_OK; }
+    if (field == GBP_F_FILE_INDEX) { memcpy(host_dst, h->h_file_of_factor.data(), need); return GBP_OK; }
+    if (fi.indexed != 2) {
+        CU(cudaMemcpyAsync(host_dst, field_dev_ptr(h, field), need, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return GBP_OK;
+    }
+    DevBuf<uint32_t> tmp;
+    CU(tmp.alloc((size_t)rows * fi.words));
+    const long long n = rows * fi.words;
+    if (field == GBP_F_JACOBIAN_B) {
+        export_jb_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->slot_of_factor.p, rows, h->linpoint.p, h->z.p, h->K,
+                                                                            reinterpret_cast<double*>(tmp.p));
+    } else {
+        gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(tmp.p, reinterpret_cast<const uint32_t*>(field_dev_ptr(h, field)),
+                                                                           h->slot_of_factor.p, rows, fi.words);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_dst, tmp.p, need, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    tmp.release();
+    if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "read field %d: %s", field, cudaGetErrorString(e));
+    return GBP_OK;
+}
+
+int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes) {
+    CHECK_H(h);
+    FieldInfo fi;
+    if (!field_info(field, &fi)) return fail(GBP_ERR_INVALID, "unknown field %d", field);
+    if (!fi.writable) return fail(GBP_ERR_INVALID, "field %d is read-only", field);
+    const long long rows = fi.indexed == 0 ? h->C : fi.indexed == 1 ? h->L : h->F;
+    const size_t need = (size_t)rows * fi.words * 4;
+    if (bytes != need) return fail(GBP_ERR_INVALID, "field %d: expected %zu bytes, got %zu", field, need, bytes);
+    if (need == 0) return GBP_OK;
+    if (!host_src) return fail(GBP_ERR_INVALID, "null source");
+    if (fi.indexed != 2) {
+        CU(cudaMemcpyAsync(field_dev_ptr(h, field), host_src, need, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (field == GBP_F_CAM_PRIOR || field == GBP_F_LMK_PRIOR) h->priors_set = true;
+        return GBP_OK;
+    }
+    DevBuf<uint32_t> tmp;
+    CU(tmp.alloc((size_t)rows * fi.words));
+    const long long n = rows * fi.words;
+    cudaError_t e = cudaMemcpyAsync(tmp.p, host_src, need, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<uint32_t*>(field_dev_ptr(h, field)), tmp.p,
+                                                                            h->slot_of_factor.p, rows, fi.words);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    tmp.release();
+    if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "write field %d: %s", field, cudaGetErrorString(e));
+    return GBP_OK;
+}
+
+int gbp_ba_fill_iters(gbp_handle h, int32_t value) {
+    CHECK_H(h);
+    if (value < 0) return fail(GBP_ERR_INVALID, "iters_since_relin must be >= 0");
+    if (h->n_slots > 0) {
+        fill_iters_kernel<<<(unsigned)((h->n_slots + 255) / 256), 256, 0, h->stream>>>(h->iters.p, h->n_slots, value);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    return GBP_OK;
+}
+
+int gbp_ba_device_ptr(gbp_handle h, int field, void** dev_ptr, size_t* bytes) {
+    if (!h || !dev_ptr) return fail(GBP_ERR_INVALID, "null argument");
+    FieldInfo fi;
+    if (!field_info(field, &fi) || fi.indexed == 2) return fail(GBP_ERR_INVALID, "field %d has no stable device layout", field);
+    *dev_ptr = field_dev_ptr(h, field);
+    if (bytes) *bytes = (size_t)(fi.indexed == 0 ? h->C : h->L) * fi.words * 4;
+    return GBP_OK;
+}
+
+int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num_undamped_iters, int32_t min_linear_iters) {
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    h->cfg.eta_damping = eta_damping; h->cfg.beta = beta;
+    h->cfg.num_undamped_iters = num_undamped_iters; h->cfg.min_linear_iters = min_linear_iters;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);  // parameters are baked into captured launches
+    h->graphs.clear();
+    return GBP_OK;
+}
+
+int gbp_ba_synchronize(gbp_handle h) {
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return GBP_OK;
+}
+
+int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_relin, int per_kernel, float* ms_total,
+                           float* ms_msg_kernel) {
+    CHECK_H(h);
+    if (n_iters <= 0) return fail(GBP_ERR_INVALID, "n_iters must be > 0");
+    if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set");
+    const int st = iteration_stages(robustify, local_relin);
+    if (ms_total) *ms_total = 0.f;
+    if (ms_msg_kernel) *ms_msg_kernel = 0.f;
+    if (!per_kernel) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        cudaGraphExec_t exec;
+        int rc = get_graph(h, st, &exec);
+        if (rc != GBP_OK) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaEventRecord(e0, h->stream));
+        for (int i = 0; i < n_iters; ++i) CU(cudaGraphLaunch(exec, h->stream));
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaEventSynchronize(e1));
+        h->launches += 2LL * n_iters;
+        if (ms_total) CU(cudaEventElapsedTime(ms_total, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return GBP_OK;
+    }
+    std::vector<cudaEvent_t> ev((size_t)2 * n_iters + 2);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventRecord(ev[2 * n_iters], h->stream));
+    for (int i = 0; i < n_iters; ++i) {
+        CU(cudaEventRecord(ev[2 * i], h->stream));
+        int rc = launch_sweep(h, st);
+        if (rc != GBP_OK) return rc;
+        CU(cudaEventRecord(ev[2 * i + 1], h->stream));
+        rc = launch_belief(h, 1);
+        if (rc != GBP_OK) return rc;
+    }
+    CU(cudaEventRecord(ev[2 * n_iters + 1], h->stream));
+    CU(cudaEventSynchronize(ev[2 * n_iters + 1]));
+    float tot = 0.f, acc = 0.f;
+    CU(cudaEventElapsedTime(&tot, ev[2 * n_iters], ev[2 * n_iters + 1]));
+    for (int i = 0; i < n_iters; ++i) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+        acc += t;
+    }
+    if (ms_total) *ms_total = tot;
+    if (ms_msg_kernel) *ms_msg_kernel = acc;
+    for (auto& e : ev) cudaEventDestroy(e);
+    return GBP_OK;
+}
+
+int64_t gbp_ba_launch_count(gbp_handle h) { return h ? h->launches : 0; }
+
+int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int device, double* out_h, double* out_J) {
+    if (!x || !K || !out_h || !out_J || n < 0) return fail(GBP_ERR_INVALID, "bad argument");
+    if (gbp_device_count() <= 0) return fail(GBP_ERR_NO_DEVICE, "no CUDA device visible: gbp_b200 has no CPU fallback");
+    if (n == 0) return GBP_OK;
+    CU(cudaSetDevice(device));
+    DevBuf<double> dx, dh, dj;
+    CU(dx.alloc((size_t)n * 9)); CU(dh.alloc((size_t)n * 2)); CU(dj.alloc((size_t)n * 18));
+    cudaError_t e = cudaMemcpy(dx.p, x, (size_t)n * 72, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        reprojection_eval_kernel<<<(unsigned)((n + 127) / 128), 128>>>(dx.p, n, Intrinsics{K[0], K[1], K[2], K[3]}, dh.p, dj.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_h, dh.p, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_J, dj.p, (size_t)n * 144, cudaMemcpyDeviceToHost);
+    dx.release(); dh.release(); dj.release();
+    if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "reprojection_eval: %s", cudaGetErrorString(e));
+    return GBP_OK;
+}
+
+}  // extern "C"

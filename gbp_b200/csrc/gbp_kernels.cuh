@@ -1,0 +1,597 @@
+// gbp_kernels.cuh -- sm_100a kernels of the GBP bundle-adjustment sweep.
+//
+// Data layout in HBM (all float64 unless noted; "slot" = position of an edge in the
+// engine's storage order, tile t owns slots [t*T, t*T + count)):
+//   msg_cam   [slots][27]  factor->keyframe message  eta[6] | Lambda packed[21]
+//   msg_lmk   [slots][9]   factor->landmark message  eta[3] | Lambda packed[6]
+//   linpoint  [slots][9]   linearisation point [t, w, y]
+//   z         [slots][2]   measurement
+//   lmk_idx   [slots] i32, iters [slots] i32, flags [slots] i32, sigma2a [slots]
+//   cam_belief[C][33]      eta[6] | Lambda[21] | mu[6]      (264 B rows)
+//   lmk_belief[L][12]      eta[3] | Lambda[6]  | mu[3]      (96 B rows = 3 sectors, 32 B aligned)
+//   cam_prior [C][27], lmk_prior[L][9]
+//   tile_partial[tiles][27] per-tile sum of new factor->keyframe messages
+// Every tile belongs to exactly ONE keyframe, so the keyframe belief is a CTA-uniform
+// broadcast and the keyframe-side sum is a plain per-tile column sum (no atomics,
+// deterministic).  Tiles are ordered landmark-block-major so that the 96 B landmark
+// belief rows gathered by a wave of CTAs stay L2-resident.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gbp_math.cuh"
+
+namespace gbp {
+
+constexpr int CAM_B = 33, LMK_B = 12, CAM_M = 27, LMK_M = 9;
+
+enum : int { ST_ROBUSTIFY = 1, ST_RELIN = 2, ST_MESSAGES = 4, ST_BELIEFS = 8, ST_LOCAL_DAMPING = 16 };
+
+struct Tile {
+    int cam;    // keyframe of every edge in the tile
+    int count;  // valid edges (<= T)
+};
+
+struct SweepParams {
+    const Tile* tiles;
+    const int* lmk_idx;
+    const double* z;
+    double* linpoint;
+    double* msg_cam;
+    double* msg_lmk;
+    int* iters;
+    int* flags;
+    double* sigma2a;
+    const double* cam_belief;
+    const double* lmk_belief;
+    double* tile_partial;
+    Intrinsics K;
+    double var0, eta_damping, beta, nstds;
+    int num_undamped, min_linear, loss, stages;
+    int n_tiles;
+};
+
+// cooperative, coalesced copy of n doubles (16 B vectors where possible; both pointers 16 B aligned)
+template <int T>
+__device__ __forceinline__ void coop_copy(double* __restrict__ dst, const double* __restrict__ src, int n) {
+    const int n2 = n >> 1;
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int i = threadIdx.x; i < n2; i += T) d2[i] = s2[i];
+    if ((n & 1) && threadIdx.x == 0) dst[n - 1] = src[n - 1];
+}
+
+// ----------------------------------------------------------------------------------------
+// K1-K3 (+ the keyframe half of K4): robustify -> relinearise -> factor-to-variable messages
+// -> per-tile sum of the messages to the keyframe.   One CTA per tile, one thread per edge.
+// Replaces gbp/gbp.py:82-84,296-332 / 64-80,267-294 / 46-54,334-373 for reprojection factors.
+// ----------------------------------------------------------------------------------------
+template <int T, bool ROBUST>
+__global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) double smem[];
+    double* s_mc = smem;                 // [T][27]
+    double* s_ml = s_mc + T * CAM_M;     // [T][9]
+    double* s_lp = s_ml + T * LMK_M;     // [T][9]
+    double* s_cb = s_lp + T * 9;         // [33] keyframe belief (+pad to 34)
+    double* s_red = s_cb + 34;           // [T/32][27]
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    const Tile tl = p.tiles[tile];
+    const int n = tl.count;
+    const long long base = (long long)tile * T;
+
+    coop_copy<T>(s_mc, p.msg_cam + base * CAM_M, n * CAM_M);
+    coop_copy<T>(s_ml, p.msg_lmk + base * LMK_M, n * LMK_M);
+    coop_copy<T>(s_lp, p.linpoint + base * 9, n * 9);
+    if (tid < CAM_B) s_cb[tid] = p.cam_belief[(long long)tl.cam * CAM_B + tid];
+    __syncthreads();
+
+    bool relin = false;
+    if (tid < n) {
+        const long long e = base + tid;
+        const int lmk = p.lmk_idx[e];
+        int it = p.iters[e];
+        int fl = p.flags[e];
+        const double2 zz = reinterpret_cast<const double2*>(p.z)[e];
+        const double z[2] = {zz.x, zz.y};
+        double bl[LMK_B];
+        {
+            const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
+#pragma unroll
+            for (int k = 0; k < LMK_B / 2; ++k) {
+                const double2 v = __ldg(src + k);
+                bl[2 * k] = v.x;
+                bl[2 * k + 1] = v.y;
+            }
+        }
+        double* my_lp = s_lp + tid * 9;
+        double* my_mc = s_mc + tid * CAM_M;
+        double* my_ml = s_ml + tid * LMK_M;
+        double x0[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) x0[k] = my_lp[k];
+
+        // --- relinearisation test (gbp/gbp.py:72-75): |linpoint - [mu_cam, mu_lmk]| > beta
+        if (p.stages & ST_RELIN) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double d = x0[k] - s_cb[27 + k];
+                d2 += d * d;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double d = x0[6 + k] - bl[9 + k];
+                d2 += d * d;
+            }
+            relin = (sqrt(d2) > p.beta) && (it >= p.min_linear);
+        }
+
+        double var = p.var0;
+        double J[18], h0[2];
+        bool lin_done = false;
+        if (ROBUST) {
+            var = p.sigma2a[e];
+            if (p.stages & ST_ROBUSTIFY) {
+                // robustify_loss uses h at the STORED linearisation point (gbp/gbp.py:309-312)
+                double r0, r1;
+                if (relin) {
+                    double hold[2];
+                    meas_fn(p.K, x0, hold);
+                    r0 = z[0] - hold[0];
+                    r1 = z[1] - hold[1];
+                } else {
+                    linearise(p.K, x0, J, h0);
+                    lin_done = true;
+                    r0 = z[0] - h0[0];
+                    r1 = z[1] - h0[1];
+                }
+                bool rf;
+                var = robust_variance(p.loss, p.var0, p.nstds, r0, r1, &rf);
+                fl = rf ? (fl | 2) : (fl & ~2);
+                p.sigma2a[e] = var;
+            }
+        }
+
+        if (p.stages & ST_RELIN) {
+            if (relin) {   // gbp/gbp.py:76-78
+#pragma unroll
+                for (int k = 0; k < 6; ++k) x0[k] = s_cb[27 + k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) x0[6 + k] = bl[9 + k];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];
+                it = 0;
+                fl &= ~1;
+                lin_done = false;
+            } else {
+                it += 1;   // gbp/gbp.py:80
+            }
+        }
+
+        if (p.stages & ST_MESSAGES) {
+            if (!lin_done) linearise(p.K, x0, J, h0);
+            double b[2];
+            factor_rhs(J, x0, z, h0, b);
+            double damping = p.eta_damping;
+            if (p.stages & ST_LOCAL_DAMPING) {   // gbp/gbp.py:49-52
+                if (it == p.num_undamped) fl |= 1;
+                damping = (fl & 1) ? p.eta_damping : 0.0;
+            }
+            // message to the landmark: marginalise the keyframe (6x6 Cholesky)
+            double nl_eta[3], nl_lam[6];
+            {
+                double P[21], ev[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ev[k] = s_cb[k] - my_mc[k];
+#pragma unroll
+                for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
+                message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
+            }
+            // message to the keyframe: marginalise the landmark (3x3 Cholesky); written in place
+            {
+                double P[6], ev[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ev[k] = bl[k] - my_ml[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) P[k] = bl[3 + k] - my_ml[3 + k];
+                message<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) my_ml[k] = nl_eta[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) my_ml[3 + k] = nl_lam[k];
+        }
+        p.iters[e] = it;
+        p.flags[e] = fl;
+    }
+    const int any_relin = __syncthreads_or(relin ? 1 : 0);
+
+    if (p.stages & ST_MESSAGES) {
+        coop_copy<T>(p.msg_cam + base * CAM_M, s_mc, n * CAM_M);
+        coop_copy<T>(p.msg_lmk + base * LMK_M, s_ml, n * LMK_M);
+    }
+    if (any_relin) coop_copy<T>(p.linpoint + base * 9, s_lp, n * 9);
+
+    if (p.stages & ST_BELIEFS) {
+        // column sums of the tile's messages to its keyframe
+        constexpr int G = T / 32;
+        if (tid < CAM_M * G) {
+            const int col = tid % CAM_M, g = tid / CAM_M;
+            const int r1 = min(n, (g + 1) * 32);
+            double acc = 0.0;
+            for (int r = g * 32; r < r1; ++r) acc += s_mc[r * CAM_M + col];
+            s_red[g * CAM_M + col] = acc;
+        }
+        __syncthreads();
+        if (tid < CAM_M) {
+            double acc = s_red[tid];
+#pragma unroll
+            for (int g = 1; g < G; ++g) acc += s_red[g * CAM_M + tid];
+            p.tile_partial[(long long)tile * CAM_M + tid] = acc;
+        }
+    }
+}
+
+template <int T>
+constexpr size_t sweep_smem_bytes() {
+    return sizeof(double) * (size_t)(T * (CAM_M + LMK_M + 9) + 34 + (T / 32) * CAM_M);
+}
+
+// ----------------------------------------------------------------------------------------
+// K4: VariableNode.update_belief (gbp/gbp.py:176-198).
+//   blocks [0, lmk_blocks): one thread per landmark, gathers its 72 B message rows through the
+//                           CSR-by-landmark slot list, adds the prior, solves mu = Lambda^-1 eta.
+//   blocks [lmk_blocks, ..): one warp per keyframe, lane k sums component k of the per-tile
+//                           partial sums (fixed order), writes the local partial for multi-GPU
+//                           exchange and, when `finalise`, the belief row.
+// ----------------------------------------------------------------------------------------
+struct BeliefParams {
+    const double* msg_lmk;
+    const double* lmk_prior;
+    double* lmk_belief;
+    const int* lmk_ptr;      // [L+1]
+    const int* lmk_slots;    // [F]
+    const double* tile_partial;
+    const int* cam_tile_ptr; // [C+1]
+    const int* cam_tiles;    // [n_tiles]
+    const double* cam_prior;
+    double* cam_belief;
+    double* cam_partial;     // [C][27]
+    int L, C, lmk_blocks, finalise;
+};
+
+__device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row) {
+    // lanes 0..26 hold eta[6] | Lambda[21]; gather to lane 0, solve, write the 33-double row
+    double v[CAM_M];
+#pragma unroll
+    for (int k = 0; k < CAM_M; ++k) v[k] = __shfl_sync(0xffffffffu, acc, k);
+    if (lane < CAM_M) row[lane] = acc;
+    if (lane == 0) {
+        double mu[6];
+        spd_solve<6>(v + 6, v, mu);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) row[27 + k] = mu[k];
+    }
+}
+
+__global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
+    if ((int)blockIdx.x < p.lmk_blocks) {
+        const int l = blockIdx.x * 128 + threadIdx.x;
+        if (l >= p.L) return;
+        double acc[LMK_M];
+#pragma unroll
+        for (int k = 0; k < LMK_M; ++k) acc[k] = p.lmk_prior[(long long)l * LMK_M + k];
+        const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
+        for (int q = p0; q < p1; ++q) {
+            const double* row = p.msg_lmk + (long long)p.lmk_slots[q] * LMK_M;
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += __ldg(row + k);
+        }
+        double mu[3];
+        spd_solve<3>(acc + 3, acc, mu);
+        double2* dst = reinterpret_cast<double2*>(p.lmk_belief + (long long)l * LMK_B);
+        dst[0] = make_double2(acc[0], acc[1]);
+        dst[1] = make_double2(acc[2], acc[3]);
+        dst[2] = make_double2(acc[4], acc[5]);
+        dst[3] = make_double2(acc[6], acc[7]);
+        dst[4] = make_double2(acc[8], mu[0]);
+        dst[5] = make_double2(mu[1], mu[2]);
+    } else {
+        const int warp = ((int)blockIdx.x - p.lmk_blocks) * 4 + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (warp >= p.C) return;
+        const int c = warp;
+        double acc = 0.0;
+        if (lane < CAM_M) {
+            const int t0 = p.cam_tile_ptr[c], t1 = p.cam_tile_ptr[c + 1];
+            for (int q = t0; q < t1; ++q) acc += p.tile_partial[(long long)p.cam_tiles[q] * CAM_M + lane];
+            p.cam_partial[(long long)c * CAM_M + lane] = acc;
+            acc += p.cam_prior[(long long)c * CAM_M + lane];
+        }
+        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B);
+    }
+}
+
+// keyframe beliefs from gathered per-rank partial sums (multi-GPU): prior + sum_r partial[r]
+__global__ void __launch_bounds__(128) cam_update_kernel(const double* __restrict__ partials, int nranks, int C,
+                                                         const double* __restrict__ cam_prior,
+                                                         double* __restrict__ cam_belief) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double acc = 0.0;
+    if (lane < CAM_M) {
+        for (int r = 0; r < nranks; ++r) acc += partials[((long long)r * C + c) * CAM_M + lane];
+        acc += cam_prior[(long long)c * CAM_M + lane];
+    }
+    cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B);
+}
+
+// ----------------------------------------------------------------------------------------
+// K5: BAFactorGraph.are / FactorGraph.energy / relinearisation count
+//     (gbp/gbp_ba.py:61-69, gbp/gbp.py:36-44,251-259, ba.py:97-100)
+// ----------------------------------------------------------------------------------------
+struct MetricParams {
+    const Tile* tiles;
+    const int* lmk_idx;
+    const double* z;
+    const int* iters;
+    const double* sigma2a;
+    const double* cam_belief;
+    const double* lmk_belief;
+    double* tile_metric;  // [n_tiles][3]
+    Intrinsics K;
+    double var0;
+    int robust;
+};
+
+template <int T>
+__global__ void __launch_bounds__(T) metric_kernel(const MetricParams p) {
+    __shared__ double s_R[9], s_t[3];
+    __shared__ double s_w[3][T / 32];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const Tile tl = p.tiles[tile];
+    const long long base = (long long)tile * T;
+    if (tid == 0) {
+        const double* row = p.cam_belief + (long long)tl.cam * CAM_B + 27;
+        double w[3] = {row[3], row[4], row[5]};
+        double R[9];
+        so3exp(w, R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_R[k] = R[k];
+        s_t[0] = row[0]; s_t[1] = row[1]; s_t[2] = row[2];
+    }
+    __syncthreads();
+    double a = 0.0, en = 0.0, cnt = 0.0;
+    if (tid < tl.count) {
+        const long long e = base + tid;
+        const double* lrow = p.lmk_belief + (long long)p.lmk_idx[e] * LMK_B + 9;
+        const double y[3] = {lrow[0], lrow[1], lrow[2]};
+        double R[9], t[3], h[2], pp[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = s_R[k];
+        t[0] = s_t[0]; t[1] = s_t[1]; t[2] = s_t[2];
+        project(p.K, R, t, y, h, pp);
+        const double r0 = h[0] - p.z[2 * e], r1 = h[1] - p.z[2 * e + 1];
+        a = sqrt(r0 * r0 + r1 * r1);
+        const double var = p.robust ? p.sigma2a[e] : p.var0;
+        en = 0.5 * (a * a) / var;
+        cnt = (p.iters[e] == 0) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        en += __shfl_down_sync(0xffffffffu, en, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if ((tid & 31) == 0) {
+        s_w[0][tid >> 5] = a; s_w[1][tid >> 5] = en; s_w[2][tid >> 5] = cnt;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        double v = 0.0;
+#pragma unroll
+        for (int g = 0; g < T / 32; ++g) v += s_w[tid][g];
+        p.tile_metric[(long long)tile * 3 + tid] = v;
+    }
+}
+
+// deterministic final reduction of [n][W] rows into out[W]   (one block of 256 threads)
+template <int W>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restrict__ rows, int n, double* __restrict__ out) {
+    __shared__ double s[W][256];
+    double acc[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256)
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[k] += rows[(long long)i * W + k];
+#pragma unroll
+    for (int k = 0; k < W; ++k) s[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o)
+#pragma unroll
+            for (int k = 0; k < W; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < W) out[threadIdx.x] = s[threadIdx.x][0];
+}
+
+// ----------------------------------------------------------------------------------------
+// K6: BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34)
+// ----------------------------------------------------------------------------------------
+// per edge: largest entry of Lambda_f = J^T J / var (for a PSD matrix: its largest diagonal entry)
+template <int T>
+__global__ void __launch_bounds__(T) edge_lammax_kernel(const Tile* tiles, const double* linpoint, const double* sigma2a,
+                                                        int robust, double var0, Intrinsics K, double* edge_max,
+                                                        double* tile_max) {
+    __shared__ double s_w[T / 32];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const Tile tl = tiles[tile];
+    const long long e = (long long)tile * T + tid;
+    double m = 0.0;
+    if (tid < tl.count) {
+        double x0[9], J[18], h0[2];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) x0[k] = linpoint[e * 9 + k];
+        linearise(K, x0, J, h0);
+        const double var = robust ? sigma2a[e] : var0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) m = fmax(m, (J[k] * J[k] + J[9 + k] * J[9 + k]) / var);
+        edge_max[e] = m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) s_w[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 1; g < T / 32; ++g) m = fmax(m, s_w[g]);
+        tile_max[tile] = m;
+    }
+}
+
+__global__ void cam_max_kernel(const double* tile_max, const int* cam_tile_ptr, const int* cam_tiles, int C, double* cam_max) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = 0.0;
+    for (int q = cam_tile_ptr[c]; q < cam_tile_ptr[c + 1]; ++q) m = fmax(m, tile_max[cam_tiles[q]]);
+    cam_max[c] = m;
+}
+
+// prior rows: Lambda = I * max / weaker^2, eta = Lambda mu   (mu = current mean stored in the belief row)
+__global__ void cam_prior_kernel(const double* cam_max, double weaker, int C, const double* cam_belief, double* cam_prior) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double lam = cam_max[c] / (weaker * weaker);
+    double* row = cam_prior + (long long)c * CAM_M;
+    for (int k = 0; k < CAM_M; ++k) row[k] = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        row[6 + sidx<6>(i, i)] = lam;
+        row[i] = lam * cam_belief[(long long)c * CAM_B + 27 + i];
+    }
+}
+
+__global__ void lmk_prior_kernel(const double* edge_max, const int* lmk_ptr, const int* lmk_slots, double weaker, int L,
+                                 const double* lmk_belief, double* lmk_prior) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double m = 0.0;
+    for (int q = lmk_ptr[l]; q < lmk_ptr[l + 1]; ++q) m = fmax(m, edge_max[lmk_slots[q]]);
+    const double lam = m / (weaker * weaker);
+    double* row = lmk_prior + (long long)l * LMK_M;
+    for (int k = 0; k < LMK_M; ++k) row[k] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        row[3 + sidx<3>(i, i)] = lam;
+        row[i] = lam * lmk_belief[(long long)l * LMK_B + 9 + i];
+    }
+}
+
+// set_priors_var (gbp/gbp_ba.py:44-52): eta = Lambda mu for given packed Lambda
+template <int N>
+__global__ void prior_eta_kernel(int V, const double* belief, int brow, int mu_off, double* prior) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    constexpr int W = N + N * (N + 1) / 2;
+    double* row = prior + (long long)v * W;
+    const double* mu = belief + (long long)v * brow + mu_off;
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < N; ++j) s += row[N + sym<N>(i, j)] * mu[j];
+        row[i] = s;
+    }
+}
+
+__global__ void scale_kernel(double* x, long long n, double f) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= f;
+}
+
+// ----------------------------------------------------------------------------------------
+// initialisation and field access
+// ----------------------------------------------------------------------------------------
+// linpoint = [mu0_cam, mu0_lmk] (gbp/gbp_ba.py:136-137); iters_since_relin = 1, flags = 0 (gbp/gbp.py:248-249)
+template <int T>
+__global__ void __launch_bounds__(T) init_edges_kernel(const Tile* tiles, const int* lmk_idx, const double* cam_belief,
+                                                       const double* lmk_belief, double var0, double* linpoint,
+                                                       int* iters, int* flags, double* sigma2a) {
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const Tile tl = tiles[tile];
+    const long long e = (long long)tile * T + tid;
+    if (tid < tl.count) {
+        const double* cm = cam_belief + (long long)tl.cam * CAM_B + 27;
+        const double* lm = lmk_belief + (long long)lmk_idx[e] * LMK_B + 9;
+        for (int k = 0; k < 6; ++k) linpoint[e * 9 + k] = cm[k];
+        for (int k = 0; k < 3; ++k) linpoint[e * 9 + 6 + k] = lm[k];
+        iters[e] = 1;
+    } else {
+        for (int k = 0; k < 9; ++k) linpoint[e * 9 + k] = 0.0;
+        iters[e] = -1;
+    }
+    flags[e] = 0;
+    sigma2a[e] = var0;
+}
+
+// belief rows from initial means: eta = 0, Lambda = 0, mu = mu0 (gbp/gbp.py:165-168, gbp/gbp_ba.py:116,123)
+__global__ void init_belief_kernel(const double* mu0, int V, int N, int brow, double* belief) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double* row = belief + (long long)v * brow;
+    for (int k = 0; k < brow - N; ++k) row[k] = 0.0;
+    for (int k = 0; k < N; ++k) row[brow - N + k] = mu0[(long long)v * N + k];
+}
+
+// dst[f][w] = src[slot_of_factor[f]][w]  (rows of W 4-byte words)
+__global__ void gather_rows_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                   const int* __restrict__ slot_of_factor, long long F, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * W) return;
+    const long long f = i / W;
+    const int w = (int)(i - f * W);
+    dst[i] = src[(long long)slot_of_factor[f] * W + w];
+}
+__global__ void scatter_rows_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src,
+                                    const int* __restrict__ slot_of_factor, long long F, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * W) return;
+    const long long f = i / W;
+    const int w = (int)(i - f * W);
+    dst[(long long)slot_of_factor[f] * W + w] = src[i];
+}
+__global__ void fill_iters_kernel(int* iters, long long n_slots, int value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots && iters[i] >= 0) iters[i] = value;
+}
+
+// J[2x9] | b[2] of every factor at its linearisation point, factor order (GBP_F_JACOBIAN_B)
+__global__ void export_jb_kernel(const int* slot_of_factor, long long F, const double* linpoint, const double* z,
+                                 Intrinsics K, double* out) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const long long e = slot_of_factor[f];
+    double x0[9], J[18], h0[2], b[2];
+    for (int k = 0; k < 9; ++k) x0[k] = linpoint[e * 9 + k];
+    linearise(K, x0, J, h0);
+    const double zz[2] = {z[2 * e], z[2 * e + 1]};
+    factor_rhs(J, x0, zz, h0, b);
+    for (int k = 0; k < 18; ++k) out[f * 20 + k] = J[k];
+    out[f * 20 + 18] = b[0];
+    out[f * 20 + 19] = b[1];
+}
+
+// standalone reprojection model (parity tests of meas_fn / jac_fn)
+__global__ void reprojection_eval_kernel(const double* x, long long n, Intrinsics K, double* out_h, double* out_J) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x0[9], J[18], h0[2];
+    for (int k = 0; k < 9; ++k) x0[k] = x[i * 9 + k];
+    linearise(K, x0, J, h0);
+    out_h[2 * i] = h0[0];
+    out_h[2 * i + 1] = h0[1];
+    for (int k = 0; k < 18; ++k) out_J[i * 18 + k] = J[k];
+}
+
+}  // namespace gbp

@@ -1,0 +1,170 @@
+"""BAEngine: thin object wrapper over one libgbp_b200 handle (one GPU, one stream).
+
+All numerics run in the CUDA library; this class only marshals NumPy arrays across the C
+ABI and unpacks the packed row formats.  It is what ``gbp_b200.ba.BAFactorGraph`` (the
+mirror of the reference's ``gbp/gbp_ba.py``) drives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+_IU6 = np.triu_indices(6)
+_IU3 = np.triu_indices(3)
+
+
+def unpack_sym(packed, n):
+    """[..., n(n+1)/2] packed upper triangle -> [..., n, n] symmetric."""
+    iu = _IU6 if n == 6 else _IU3 if n == 3 else np.triu_indices(n)
+    out = np.zeros(packed.shape[:-1] + (n, n))
+    out[..., iu[0], iu[1]] = packed
+    out[..., iu[1], iu[0]] = packed
+    return out
+
+
+def pack_sym(full):
+    n = full.shape[-1]
+    iu = _IU6 if n == 6 else _IU3 if n == 3 else np.triu_indices(n)
+    return np.ascontiguousarray(full[..., iu[0], iu[1]])
+
+
+class BAEngine:
+    def __init__(self, cam_id, lmk_id, z, cam_mu0, lmk_mu0, K4, configs, device=0, stream=None,
+                 tile_edges=0, lmk_block=0):
+        lib = L.load()
+        self._lib = lib
+        self._h = None
+        cam_id = np.ascontiguousarray(cam_id, dtype=np.int32)
+        lmk_id = np.ascontiguousarray(lmk_id, dtype=np.int32)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        cam_mu0 = np.ascontiguousarray(cam_mu0, dtype=np.float64).reshape(-1, 6)
+        lmk_mu0 = np.ascontiguousarray(lmk_mu0, dtype=np.float64).reshape(-1, 3)
+        K4 = np.ascontiguousarray(K4, dtype=np.float64).reshape(4)
+        if not (len(cam_id) == len(lmk_id) == len(z)):
+            raise ValueError("cam_id, lmk_id and z must have one row per measurement")
+        loss = configs.get("loss", None)
+        if loss not in L.LOSS_CODES:
+            raise ValueError(f"unknown loss {loss!r} (None, 'huber' or 'constant')")
+        cfg = L.GbpConfig(float(configs["gauss_noise_std"]), float(configs["eta_damping"]), float(configs["beta"]),
+                          float(configs.get("Nstds", 3.0)), int(configs["num_undamped_iters"]),
+                          int(configs["min_linear_iters"]), L.LOSS_CODES[loss], int(tile_edges), int(lmk_block), 0)
+        self.cfg = cfg
+        h = C.c_void_p()
+        L.check(lib.gbp_ba_create(C.byref(cfg), len(cam_mu0), len(lmk_mu0), len(cam_id), L.ptr(cam_id), L.ptr(lmk_id),
+                                  L.ptr(z), L.ptr(cam_mu0), L.ptr(lmk_mu0), L.ptr(K4), int(device),
+                                  C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        sizes = (C.c_int64 * 6)()
+        L.check(lib.gbp_ba_sizes(h, sizes))
+        self.C, self.L, self.F, self.n_tiles, self.tile_edges, self.n_slots = [int(v) for v in sizes]
+        self.K4 = K4
+        self.device = int(device)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if self._h is not None:
+            self._lib.gbp_ba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ priors
+    def prior_scan(self):
+        out = np.zeros(self.C)
+        L.check(self._lib.gbp_ba_prior_scan(self._h, L.ptr(out)))
+        return out
+
+    def generate_priors(self, weaker_factor, cam_max=None):
+        cm = None if cam_max is None else np.ascontiguousarray(cam_max, dtype=np.float64)
+        L.check(self._lib.gbp_ba_generate_priors(self._h, float(weaker_factor), L.ptr(cm)))
+
+    def set_priors(self, cam_lam_packed, lmk_lam_packed):
+        a = np.ascontiguousarray(cam_lam_packed, dtype=np.float64).reshape(self.C, 21)
+        b = np.ascontiguousarray(lmk_lam_packed, dtype=np.float64).reshape(self.L, 6)
+        L.check(self._lib.gbp_ba_set_priors(self._h, L.ptr(a), L.ptr(b)))
+
+    def scale_priors(self, f):
+        L.check(self._lib.gbp_ba_scale_priors(self._h, float(f)))
+
+    # ------------------------------------------------------------------ sweeps
+    def sweep_local(self, stages):
+        L.check(self._lib.gbp_ba_sweep_local(self._h, int(stages)))
+
+    def cam_update(self, partials_dev_ptr=None, nranks=1):
+        L.check(self._lib.gbp_ba_cam_update(self._h, C.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
+                                            int(nranks)))
+
+    def iterate(self, n_iters=1, robustify=False, local_relin=True):
+        L.check(self._lib.gbp_ba_iterate(self._h, int(n_iters), int(bool(robustify)), int(bool(local_relin))))
+
+    def update_beliefs(self):
+        L.check(self._lib.gbp_ba_update_beliefs(self._h))
+
+    def metrics(self):
+        """(sum of |r|, energy, number of factors with iters_since_relin == 0) over the local edges."""
+        out = (C.c_double * 3)()
+        L.check(self._lib.gbp_ba_metrics(self._h, out))
+        return float(out[0]), float(out[1]), int(round(out[2]))
+
+    def fill_iters(self, value):
+        L.check(self._lib.gbp_ba_fill_iters(self._h, int(value)))
+
+    def set_params(self, eta_damping, beta, num_undamped_iters, min_linear_iters):
+        L.check(self._lib.gbp_ba_set_params(self._h, float(eta_damping), float(beta), int(num_undamped_iters),
+                                            int(min_linear_iters)))
+
+    def synchronize(self):
+        L.check(self._lib.gbp_ba_synchronize(self._h))
+
+    def time_iterations(self, n_iters, robustify=True, local_relin=True, per_kernel=False):
+        a, b = C.c_float(), C.c_float()
+        L.check(self._lib.gbp_ba_time_iterations(self._h, int(n_iters), int(bool(robustify)), int(bool(local_relin)),
+                                                 int(bool(per_kernel)), C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def launch_count(self):
+        return int(self._lib.gbp_ba_launch_count(self._h))
+
+    def device_ptr(self, field):
+        p, n = C.c_void_p(), C.c_size_t()
+        L.check(self._lib.gbp_ba_device_ptr(self._h, int(field), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ------------------------------------------------------------------ field access
+    def _rows(self, kind):
+        return {"C": self.C, "L": self.L, "F": self.F}[kind]
+
+    def read(self, field, out=None):
+        kind, dt, w = L.FIELD_SHAPES[field]
+        n = self._rows(kind)
+        if out is None:
+            out = np.empty((n, w), dtype=dt)
+        assert out.dtype == dt and out.size == n * w and out.flags.c_contiguous
+        L.check(self._lib.gbp_ba_read(self._h, int(field), L.ptr(out), out.nbytes))
+        return out
+
+    def write(self, field, arr):
+        kind, dt, w = L.FIELD_SHAPES[field]
+        n = self._rows(kind)
+        a = np.ascontiguousarray(arr, dtype=dt)
+        if a.size != n * w:
+            raise ValueError(f"field {field}: expected {n}x{w} values, got {a.size}")
+        L.check(self._lib.gbp_ba_write(self._h, int(field), L.ptr(a), a.nbytes))
+
+
+def reprojection_eval(x, K4, device=0):
+    """meas_fn / jac_fn of the reprojection factor evaluated by the CUDA kernels (parity tests)."""
+    lib = L.load()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 9)
+    K4 = np.ascontiguousarray(K4, dtype=np.float64).reshape(4)
+    h = np.empty((len(x), 2))
+    J = np.empty((len(x), 18))
+    L.check(lib.gbp_reprojection_eval(L.ptr(x), len(x), L.ptr(K4), int(device), L.ptr(h), L.ptr(J)))
+    return h, J.reshape(-1, 2, 9)

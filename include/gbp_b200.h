@@ -1,0 +1,173 @@
+/*
+ * gbp_b200.h  --  C ABI of libgbp_b200.so: the B200-native Gaussian Belief Propagation
+ * sweep for bundle adjustment (reprojection factors, 6-dof keyframes, 3-dof landmarks).
+ *
+ * The reference (joeaortiz/gbp) is pure Python and has NO FFI/plugin interface; its
+ * boundary for this path is the Python class API of gbp/gbp.py and gbp/gbp_ba.py.  Each
+ * entry point below therefore cites the reference METHOD it replaces (file:line under
+ * the reference tree).  The host-side Python mirror of those classes lives in
+ * gbp_b200/compat/ and calls only these functions (ctypes); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a gbp_status otherwise; gbp_last_error()
+ *     returns a thread-local description.  CUDA errors are captured, never abort().
+ *   - all host pointers are caller-owned, copied before return, never retained.
+ *   - all floating point is IEEE float64, indices are int32.
+ *   - one handle = one CUDA device + one stream; calls on a handle are not re-entrant.
+ *   - "factor order" is the reference's: camera-major, file order within a camera
+ *     (gbp/gbp_ba.py:128-143), i.e. a stable sort of the measurement list by camera id.
+ *   - symmetric matrices cross the ABI PACKED, upper triangle row-major:
+ *     6x6 -> 21 doubles, 3x3 -> 6 doubles.
+ */
+#ifndef GBP_B200_H
+#define GBP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBP_B200_ABI_VERSION 1
+
+typedef struct gbp_ba_graph* gbp_handle;
+
+typedef enum gbp_status {
+    GBP_OK = 0,
+    GBP_ERR_INVALID = 1,   /* bad argument / inconsistent graph                      */
+    GBP_ERR_CUDA = 2,      /* CUDA runtime error (message in gbp_last_error)         */
+    GBP_ERR_NO_DEVICE = 3, /* no CUDA device: there is NO CPU fallback               */
+    GBP_ERR_STATE = 4      /* call order violated (e.g. sweep before priors)         */
+} gbp_status;
+
+typedef enum gbp_loss { GBP_LOSS_NONE = 0, GBP_LOSS_HUBER = 1, GBP_LOSS_CONSTANT = 2 } gbp_loss;
+
+/* The `configs` dict of ba.py:51-60 consumed by create_ba_graph (gbp/gbp_ba.py:104-107,135)
+ * and the FactorGraph constructor (gbp/gbp.py:12-34). */
+typedef struct gbp_config {
+    double gauss_noise_std;      /* sigma of the measurement model (gbp/gbp.py:236)          */
+    double eta_damping;          /* graph-level damping (gbp/gbp.py:28)                        */
+    double beta;                 /* relinearisation threshold (gbp/gbp.py:32)                  */
+    double Nstds;                /* mahalanobis_threshold of the robust loss (gbp/gbp.py:244)  */
+    int32_t num_undamped_iters;  /* gbp/gbp.py:33                                              */
+    int32_t min_linear_iters;    /* gbp/gbp.py:34                                              */
+    int32_t loss;                /* gbp_loss (gbp/gbp.py:243)                                  */
+    int32_t tile_edges;          /* 0 = auto; else 32/64/128 edges per tile (engine tuning)    */
+    int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
+    int32_t reserved;
+} gbp_config;
+
+/* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */
+enum {
+    GBP_STAGE_ROBUSTIFY = 1, /* robustify_all_factors   gbp/gbp.py:82-84, 296-332 */
+    GBP_STAGE_RELIN = 2,     /* relinearise_factors     gbp/gbp.py:64-80          */
+    GBP_STAGE_MESSAGES = 4,  /* compute_all_messages    gbp/gbp.py:46-54, 334-373 */
+    GBP_STAGE_BELIEFS = 8,   /* update_all_beliefs      gbp/gbp.py:56-58, 176-198 */
+    GBP_STAGE_LOCAL_DAMPING = 16 /* local_relin=True: per-factor damping (gbp/gbp.py:49-52) */
+};
+
+/* Fields readable / writable through gbp_ba_read / gbp_ba_write.  Row widths in doubles
+ * unless noted; factor-indexed fields are in factor order. */
+typedef enum gbp_field {
+    GBP_F_CAM_BELIEF = 0, /* C x 33 : eta[6] | Lambda packed[21] | mu[6]   (VariableNode.belief/.mu, gbp/gbp.py:165-168) */
+    GBP_F_LMK_BELIEF = 1, /* L x 12 : eta[3] | Lambda packed[6]  | mu[3]                                                  */
+    GBP_F_CAM_PRIOR = 2,  /* C x 27 : eta[6] | Lambda packed[21]           (VariableNode.prior, gbp/gbp.py:170)           */
+    GBP_F_LMK_PRIOR = 3,  /* L x 9                                                                                        */
+    GBP_F_MSG_CAM = 4,    /* F x 27 : factor->keyframe message              (Factor.messages[0], gbp/gbp.py:228)           */
+    GBP_F_MSG_LMK = 5,    /* F x 9  : factor->landmark message              (Factor.messages[1])                           */
+    GBP_F_LINPOINT = 6,   /* F x 9  : Factor.linpoint (gbp/gbp.py:231)                                                     */
+    GBP_F_ITERS_SINCE_RELIN = 7, /* F x int32 : Factor.iters_since_relin (gbp/gbp.py:249; written by ba.py:91-93)         */
+    GBP_F_FLAGS = 8,      /* F x int32 : bit0 = per-factor damping on (Factor.eta_damping != 0), bit1 = robust_flag        */
+    GBP_F_ADAPTIVE_VAR = 9, /* F x 1 : Factor.adaptive_gauss_noise_var (gbp/gbp.py:242)                                    */
+    GBP_F_MEASUREMENT = 10, /* F x 2 : Factor.measurement (read only)                                                      */
+    GBP_F_JACOBIAN_B = 11,  /* F x 20: J[2x9] row-major | b[2] = J x0 + z - h(x0), recomputed at linpoint (read only);
+                               Factor.factor = (J^T b / var, J^T J / var)  (gbp/gbp.py:287-289)                            */
+    GBP_F_ADJ = 12,         /* F x 2 int32 : (camera id, landmark id) = Factor.adj_vIDs (landmark NOT offset by C; read only) */
+    GBP_F_FILE_INDEX = 13,  /* F x int32 : position of each factor in the measurement list passed to create (read only)    */
+    GBP_F_CAM_PARTIAL = 14, /* C x 27 : this rank's sum of factor->keyframe messages (multi-GPU exchange buffer; read only) */
+    GBP_F__COUNT
+} gbp_field;
+
+const char* gbp_last_error(void);
+int gbp_abi_version(void);
+/* Number of CUDA devices visible (0 on a CPU-only host; never an error). */
+int gbp_device_count(void);
+
+/* create_ba_graph (gbp/gbp_ba.py:97-150) after read_balfile: builds the device-resident graph from
+ * the measurement list (file order), linearises every factor at the initial means
+ * (gbp/gbp_ba.py:136-137 -> gbp/gbp.py:267-294), zero messages, iters_since_relin = 1, damping 0.
+ * `stream` is a cudaStream_t (NULL = the handle creates its own).  n_cam_total/n_lmk are the sizes
+ * of cam_mu0 / lmk_mu0; every camera id < C, landmark id < L. */
+int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F,
+                  const int32_t* cam_id, const int32_t* lmk_id, const double* z /* F x 2 */,
+                  const double* cam_mu0 /* C x 6 */, const double* lmk_mu0 /* L x 3 */,
+                  const double K[4] /* fx fy cx cy */, int device, void* stream, gbp_handle* out);
+int gbp_ba_destroy(gbp_handle h);
+
+/* Sizes: C, L, F, number of edge tiles, edges per tile, padded edge slots. */
+int gbp_ba_sizes(gbp_handle h, int64_t out[6]);
+
+/* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
+ * must be combined across ranks: call gbp_ba_prior_scan first, max-reduce the C doubles it returns
+ * over ranks, and pass them to gbp_ba_generate_priors as cam_max (NULL = use the local scan). */
+int gbp_ba_prior_scan(gbp_handle h, double* cam_max /* C, host */);
+int gbp_ba_generate_priors(gbp_handle h, double weaker_factor, const double* cam_max /* C or NULL */);
+/* BAFactorGraph.set_priors_var (gbp/gbp_ba.py:44-52): prior Lambda = given packed precision,
+ * eta = Lambda mu (current means). */
+int gbp_ba_set_priors(gbp_handle h, const double* cam_lam /* C x 21 */, const double* lmk_lam /* L x 6 */);
+/* BAFactorGraph.weaken_priors (gbp/gbp_ba.py:36-42): prior eta, Lambda *= factor. */
+int gbp_ba_scale_priors(gbp_handle h, double factor);
+
+/* One pass of the selected stages of synchronous_iteration (gbp/gbp.py:86-92) over the LOCAL edges.
+ * Without GBP_STAGE_BELIEFS nothing is reduced.  With it, landmark beliefs are updated and the local
+ * sum of factor->keyframe messages is left in GBP_F_CAM_PARTIAL; keyframe beliefs are finalised by
+ * gbp_ba_cam_update.  Everything is enqueued on the handle's stream; no host synchronisation. */
+int gbp_ba_sweep_local(gbp_handle h, int stages);
+/* Finish VariableNode.update_belief (gbp/gbp.py:176-198) for the keyframes: belief = prior + sum over
+ * ranks (in rank order) of the partial sums.  `partials` is a DEVICE pointer to nranks x C x 27
+ * doubles (e.g. the output of an NCCL all-gather of GBP_F_CAM_PARTIAL); NULL = use this handle's own
+ * partial (single GPU). */
+int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks);
+/* n x synchronous_iteration(robustify, local_relin) on one GPU (gbp/gbp.py:86-92; the loop of
+ * ba.py:84-105 without the client's per-iteration reads): sweep_local + cam_update, replayed from a
+ * CUDA graph. */
+int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin);
+/* FactorGraph.update_all_beliefs alone (gbp/gbp.py:56-58), single GPU. */
+int gbp_ba_update_beliefs(gbp_handle h);
+
+/* BAFactorGraph.are (gbp/gbp_ba.py:61-69), FactorGraph.energy (gbp/gbp.py:36-44) and the count of
+ * factors with iters_since_relin == 0 (ba.py:97-100) over the local edges.  out[0] = sum of |r|
+ * (NOT yet divided by F), out[1] = energy, out[2] = count.  Synchronises the stream. */
+int gbp_ba_metrics(gbp_handle h, double out[3]);
+
+/* Field access (synchronises the stream).  `bytes` must equal rows x row bytes of the field. */
+int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes);
+int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes);
+/* Fill every factor's iters_since_relin with `value` on the device (the loop of ba.py:91-93). */
+int gbp_ba_fill_iters(gbp_handle h, int32_t value);
+/* Raw device pointer of a variable-indexed field or GBP_F_CAM_PARTIAL (for zero-copy NCCL / torch). */
+int gbp_ba_device_ptr(gbp_handle h, int field, void** dev_ptr, size_t* bytes);
+/* Change the relinearisation / damping parameters of the FactorGraph object (gbp/gbp.py:28-34). */
+int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num_undamped_iters,
+                      int32_t min_linear_iters);
+
+int gbp_ba_synchronize(gbp_handle h);
+/* Timing helper for benchmarks: runs n_iters iterations bracketed by CUDA events on the handle's
+ * stream; *ms_total = elapsed device time, *ms_msg_kernel = summed time of the message kernel alone
+ * (measured with per-launch events when per_kernel != 0, else 0). */
+int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_relin, int per_kernel,
+                           float* ms_total, float* ms_msg_kernel);
+/* Number of kernel launches issued by this handle since creation (bench "gpu_launches"). */
+int64_t gbp_ba_launch_count(gbp_handle h);
+
+/* Standalone evaluation of the reprojection factor model on the device, for parity tests of
+ * reprojection.meas_fn / jac_fn (gbp/factors/reprojection.py:12-44): x is n x 9, out_h n x 2,
+ * out_J n x 18 (host pointers). */
+int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int device, double* out_h,
+                          double* out_J);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBP_B200_H */

@@ -1,0 +1,316 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+inputs and against the fixtures generated from the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import golden_configs, golden_problem, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+# North-star tolerance (BASELINE.json): converged beliefs within 1e-4 relative of the reference.
+TOL_CONVERGED = 1e-4
+# Early sweeps (before rounding differences have been amplified by relinearisation decisions)
+TOL_EARLY = 1e-7
+
+
+def _unpack(rows, n):
+    from gbp_b200.engine import unpack_sym
+    return rows[:, :n], unpack_sym(rows[:, n:n + n * (n + 1) // 2], n), rows[:, -n:]
+
+
+def _run_loop(graph, G, n_iters, on_iter=None):
+    """The body of ba.py:75-105 against our BAFactorGraph (per-iteration metrics like ba.py:95-101)."""
+    cfg = golden_configs(G)
+    float_impl = bool(G["float_impl"])
+    graph.generate_priors_var(weaker_factor=cfg["prior_std_weaker_factor"])
+    graph.update_all_beliefs()
+    wf = np.log10(100.0) / 5
+    are, en, nrel = [], [], []
+    for i in range(n_iters):
+        if float_impl and (i + 1) % 2 == 0 and i < 10:
+            graph.weaken_priors(wf)
+        if i == 3 or i == 8:
+            for factor in graph.factors:
+                factor.iters_since_relin = 1
+        a, e, n = graph.metrics()
+        are.append(a); en.append(e); nrel.append(n)
+        graph.synchronous_iteration(robustify=True, local_relin=True)
+        if on_iter:
+            on_iter(i)
+    a, e, n = graph.metrics()
+    are.append(a); en.append(e); nrel.append(n)
+    return np.array(are), np.array(en), np.array(nrel)
+
+
+def _check_snapshot(graph, G, key, tol):
+    from gbp_b200 import _lib as L
+    fs = G["fsample"]
+    ce, cl, cm = _unpack(graph._eng.read(L.F_CAM_BELIEF), 6)
+    le, ll, lm = _unpack(graph._eng.read(L.F_LMK_BELIEF), 3)
+    worst = {
+        "cam_mu": relerr(cm.ravel(), G[f"{key}_cam_mu"]), "lmk_mu": relerr(lm.ravel(), G[f"{key}_lmk_mu"]),
+        "cam_eta": relerr(ce.ravel(), G[f"{key}_cam_eta"]), "lmk_eta": relerr(le.ravel(), G[f"{key}_lmk_eta"]),
+        "cam_lam": relerr(cl.ravel(), G[f"{key}_cam_lam"]), "lmk_lam": relerr(ll.ravel(), G[f"{key}_lmk_lam"]),
+    }
+    mce, mcl, _ = _unpack(graph._eng.read(L.F_MSG_CAM)[fs], 6)
+    mle, mll, _ = _unpack(graph._eng.read(L.F_MSG_LMK)[fs], 3)
+    worst["msg_cam_eta"] = relerr(mce, G[f"{key}_msg_cam_eta"]); worst["msg_cam_lam"] = relerr(mcl, G[f"{key}_msg_cam_lam"])
+    worst["msg_lmk_eta"] = relerr(mle, G[f"{key}_msg_lmk_eta"]); worst["msg_lmk_lam"] = relerr(mll, G[f"{key}_msg_lmk_lam"])
+    worst["linpoint"] = relerr(graph._eng.read(L.F_LINPOINT)[fs], G[f"{key}_linpoint"])
+    assert np.array_equal(graph._eng.read(L.F_ITERS)[:, 0], G[f"{key}_iters_since_relin"]), key
+    damp = np.where(graph._eng.read(L.F_FLAGS)[:, 0] & 1, graph.eta_damping, 0.0)
+    assert np.array_equal(damp, G[f"{key}_eta_damping"]), key
+    bad = {k: v for k, v in worst.items() if not v < tol}
+    assert not bad, (key, bad)
+    return worst
+
+
+def test_reprojection_model_matches_oracle():
+    """meas_fn / jac_fn (gbp/factors/reprojection.py:12-44) evaluated by the kernels."""
+    from gbp_b200.engine import reprojection_eval
+    from oracle import gbp_oracle as O
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, size=(4096, 9))
+    x[:, 2] += 3.0           # keep the point in front of the camera
+    K4 = np.array([517.306408, 516.469215, 318.64304, 255.313989])
+    h, J = reprojection_eval(x, K4)
+    Ko = O.K_matrix(K4)
+    ho, Jo = O.meas_fn(x, Ko), O.jac_fn(x, Ko)
+    assert np.max(np.abs(h - ho) / (1 + np.abs(ho))) < 1e-12
+    assert np.max(np.abs(J - Jo) / (1 + np.abs(Jo))) < 1e-11
+
+
+def test_known_answer_factor0():
+    """SURVEY section 8(c) known answers for factor 0 of fr1desk_vsmall through the proxy objects."""
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden("fr1desk_vsmall")
+    graph = create_ba_graph(golden_problem(G), golden_configs(G))
+    f0 = graph.factors[0]
+    assert f0.adj_vIDs == [0, 47] and f0.iters_since_relin == 1 and f0.eta_damping == 0.0
+    np.testing.assert_allclose(f0.measurement, [358.3182, 189.9086], atol=1e-10)
+    fs = G["fsample"]
+    assert fs[0] == 0
+    assert relerr(f0.factor.eta, G["init_factor_eta"][0]) < 1e-12
+    assert relerr(f0.factor.lam, G["init_factor_lam"][0]) < 1e-12
+    assert abs(f0.factor.lam.max() - 90516.99360510931) < 1e-6
+    np.testing.assert_allclose(f0.linpoint, G["init_linpoint"][0], rtol=0, atol=0)
+    graph.generate_priors_var(weaker_factor=50.0)
+    assert abs(graph.cam_nodes[0].prior.lam[0, 0] - 232.48310953175482) < 1e-9
+    assert abs(graph.lmk_nodes[0].prior.lam[0, 0] - 33.684116437247276) < 1e-9
+    assert graph.lmk_nodes[0].variableID == 10
+    graph.update_all_beliefs()
+    graph.synchronous_iteration(robustify=True, local_relin=True)
+    np.testing.assert_allclose(graph.cam_nodes[0].mu, [0.1573795672, -0.1153594255, 0.3999238657, -0.1253963241,
+                                                       0.185235196, 0.0091166874], atol=2e-9)
+    np.testing.assert_allclose(graph.lmk_nodes[0].mu, [-0.5037869154, -0.0611332514, 0.6451349878], atol=2e-9)
+    np.testing.assert_allclose(f0.messages[1].eta, [27.3858176992, -16.8956565791, 8.9587025115], atol=2e-8)
+    graph.close()
+
+
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float"])
+def test_trajectory_against_reference_fixture(name):
+    """Every checkpoint of the reference run: beliefs (eta, Lambda, mu), sampled messages and
+    linearisation points, and the per-factor relinearisation / damping state, for all loss modes."""
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden(name)
+    graph = create_ba_graph(golden_problem(G), golden_configs(G))
+    cks = set(G["checkpoints"].tolist())
+    float_impl = bool(G["float_impl"])
+
+    def on_iter(i):
+        if i in cks:
+            tol = TOL_EARLY if i <= 2 else (TOL_CONVERGED if float_impl else 1e-5)
+            _check_snapshot(graph, G, f"s{i}", tol)
+
+    are, en, nrel = _run_loop(graph, G, int(G["n_iters"]), on_iter)
+    assert np.array_equal(nrel, G["n_relin"])
+    tol = TOL_CONVERGED if float_impl else 1e-6
+    assert relerr(are, G["are"]) < tol and relerr(en, G["energy"]) < tol
+    if G["cfg_vals"][list(G["cfg_keys"]).index("loss")] != "None":
+        from gbp_b200 import _lib as L
+        last = int(G["checkpoints"].max())
+        assert relerr(graph._eng.read(L.F_ADAPTIVE_VAR)[:, 0], G[f"s{last}_adaptive_var"]) < 1e-5
+    graph.close()
+
+
+def test_fr1desk_200_iterations_converged_beliefs():
+    """BASELINE config 3: fr1desk, defaults, 200 synchronous iterations; beliefs (mean AND precision)
+    within 1e-4 relative of the reference, same ARE / energy / relinearisation trace."""
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden("fr1desk")
+    graph = create_ba_graph(golden_problem(G), golden_configs(G))
+    assert (len(graph.cam_nodes), len(graph.lmk_nodes), len(graph.factors)) == (63, 2869, 13298)
+    cks = set(G["checkpoints"].tolist())
+    seen = {}
+
+    def on_iter(i):
+        if i in cks:
+            seen[i] = _check_snapshot(graph, G, f"s{i}", TOL_EARLY if i == 0 else TOL_CONVERGED)
+
+    are, en, nrel = _run_loop(graph, G, 200, on_iter)
+    assert sorted(seen) == [0, 15, 16, 99, 199]
+    assert abs(are[-1] - 1.656861417438452) < 1e-6 and abs(en[-1] - 7128.308364695148) < 1e-2
+    assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
+    assert np.max(np.abs(nrel - G["n_relin"])) <= 2, np.abs(nrel - G["n_relin"]).max()   # branch decisions
+    assert nrel[15] == 13298 and nrel[:15].sum() == 0
+    graph.close()
+
+
+@pytest.mark.parametrize("tile,block", [(32, 0), (64, 0), (128, 0), (32, 100), (128, 64)])
+def test_tiling_and_landmark_blocking_do_not_change_results(tile, block):
+    """The engine's storage order (tile size, landmark L2 blocks) is invisible in the results."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200 import _lib as L
+    G = load_golden("fr1desk_vsmall")
+    ref = create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=32, lmk_block=0)
+    alt = create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=tile, lmk_block=block)
+    for g in (ref, alt):
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+        g.iterate(20, robustify=True, local_relin=True)
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT):
+        assert relerr(alt._eng.read(f), ref._eng.read(f)) < 1e-9, f
+    assert np.array_equal(alt._eng.read(L.F_ITERS), ref._eng.read(L.F_ITERS))
+    assert np.array_equal(alt._eng.read(L.F_ADJ), ref._eng.read(L.F_ADJ))
+    ref.close(); alt.close()
+
+
+def test_synthetic_small_against_oracle():
+    """Down-scaled instance of the synthetic generator (configs 4-5): GPU vs oracle, 30 sweeps."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.synthetic import make_synthetic
+    from oracle.gbp_oracle import BAOracle, run_ba_loop
+    prob = make_synthetic(20, 2000, 10, seed=0)
+    cfg = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8,
+               eta_damping=0.4, prior_std_weaker_factor=50.0)
+    o = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, cfg)
+    are_o, en_o, nrel_o = run_ba_loop(o, 30, 50.0)
+    graph = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512)
+    G = {"cfg_keys": np.array(sorted(cfg)), "cfg_vals": np.array([str(cfg[k]) for k in sorted(cfg)]), "float_impl": 0}
+    are, en, nrel = _run_loop(graph, G, 30)
+    assert np.array_equal(nrel, nrel_o)
+    assert relerr(are, are_o) < 1e-6 and relerr(en, en_o) < 1e-6
+    mu = graph.get_means()
+    assert relerr(mu, np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])) < 1e-6
+    assert en[-1] < en[0] * 1e-3
+    graph.close()
+
+
+def test_staged_calls_equal_fused_iteration():
+    """robustify_all_factors / relinearise_factors / compute_all_messages / update_all_beliefs called
+    one by one (gbp/gbp.py:82-92) give the same state as synchronous_iteration."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200 import _lib as L
+    G = load_golden("fr1desk_vsmall_huber")
+    a = create_ba_graph(golden_problem(G), golden_configs(G))
+    b = create_ba_graph(golden_problem(G), golden_configs(G))
+    for g in (a, b):
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+    for i in range(20):
+        if i == 3:
+            a._eng.fill_iters(7); b._eng.fill_iters(7)      # make relinearisation fire early
+        a.synchronous_iteration(robustify=True, local_relin=True)
+        b.robustify_all_factors(); b.relinearise_factors(); b.compute_all_messages(local_relin=True); b.update_all_beliefs()
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ADAPTIVE_VAR):
+        assert relerr(b._eng.read(f), a._eng.read(f)) < 1e-12, f
+    assert np.array_equal(a._eng.read(L.F_ITERS), b._eng.read(L.F_ITERS))
+    assert (a._eng.read(L.F_ITERS) == 0).any() or (a._eng.read(L.F_ITERS) < 17).any()
+    a.close(); b.close()
+
+
+def test_proxy_api_surface():
+    """Attributes the reference clients touch (ba.py:70-105, vis/ba_vis.py:41-43,115)."""
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden("fr1desk_vsmall")
+    graph = create_ba_graph(golden_problem(G), golden_configs(G))
+    assert graph.n_var_nodes == 650 and graph.n_factor_nodes == 1801 and graph.n_edges == 3602
+    assert len(graph.var_nodes) == 650 and graph.var_nodes[10].variableID == 10 and graph.var_nodes[10].dofs == 3
+    assert graph.cam_nodes[3].c_id == 3 and graph.lmk_nodes[5].l_id == 5
+    assert graph.factors[0].args[0].shape == (3, 3)
+    graph.generate_priors_var(50.0)
+    graph.update_all_beliefs()
+    for factor in graph.factors:
+        factor.iters_since_relin = 5
+    graph.factors[7].iters_since_relin = 2
+    graph.synchronous_iteration(robustify=True, local_relin=True)
+    its = [f.iters_since_relin for f in graph.factors]
+    assert its[7] == 3 and its[0] == 6 and set(its) == {3, 6}
+    assert graph.factors[0].eta_damping == 0.4 and graph.factors[7].eta_damping == 0.0
+    # adjacency lists are consistent with the factors
+    v = graph.lmk_nodes[37]
+    assert all(f.adj_vIDs[1] == v.variableID for f in v.adj_factors) and len(v.adj_factors) >= 1
+    # prior write-through (ndim_posegraph.py:71-72 style assignment)
+    node = graph.cam_nodes[1]
+    node.prior.lam = np.eye(6) * 3.0
+    node.prior.eta = np.arange(6.0)
+    graph.update_all_beliefs()
+    np.testing.assert_allclose(graph.cam_nodes[1].prior.lam, np.eye(6) * 3.0)
+    lam = graph.cam_nodes[1].belief.lam
+    assert np.allclose(lam, lam.T) and np.all(np.linalg.eigvalsh(lam) > 0)
+    assert np.allclose(graph.cam_nodes[1].Sigma @ lam, np.eye(6), atol=1e-8)
+    r = graph.factors[0].compute_residual()
+    assert r.shape == (2,) and abs(np.linalg.norm(r) - graph.factors[0].reprojection_err()) < 1e-12
+    assert abs(np.mean([np.linalg.norm(x) for x in np.array(graph.compute_residuals()).reshape(-1, 2)]) - graph.are()) < 1e-9
+    graph.close()
+
+
+def test_edge_cases():
+    """Empty measurement list, a landmark seen once, a keyframe with no measurements, ragged tiles."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.balio import BALProblem
+    from gbp_b200 import _lib as L
+    from oracle.gbp_oracle import BAOracle
+    cfg = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8,
+               eta_damping=0.4)
+    G = load_golden("fr1desk_vsmall")
+    P = golden_problem(G)
+    # (a) empty graph: creation and metrics work, nothing to sweep
+    empty = create_ba_graph(BALProblem(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2)), P.cam_means[:2],
+                                       P.lmk_means[:3], P.K4), cfg)
+    assert len(empty.factors) == 0 and empty._eng.metrics() == (0.0, 0.0, 0)
+    empty.close()
+    # (b) 33 measurements of one keyframe (one full 32-tile + a tile of 1) plus an isolated keyframe;
+    #     file order deliberately NOT camera-sorted
+    sel = np.nonzero(P.cam_id == 2)[0][:33]
+    extra = np.nonzero(P.cam_id == 0)[0][:5]
+    idx = np.concatenate([sel[:10], extra, sel[10:]])
+    used = np.unique(P.lmk_id[idx])
+    remap = -np.ones(P.n_points, dtype=np.int32); remap[used] = np.arange(len(used))
+    prob = BALProblem(P.cam_id[idx], remap[P.lmk_id[idx]], P.z[idx], P.cam_means[:4], P.lmk_means[used], P.K4)
+    g = create_ba_graph(prob, cfg, tile_edges=32)
+    o = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, cfg)
+    assert np.array_equal(g._eng.read(L.F_FILE_INDEX)[:, 0], o.file_order)
+    # keyframes 1 and 3 have no measurement: give every variable an explicit prior instead
+    cov = [np.eye(6) * 0.01] * 4 + [np.eye(3) * 0.04] * len(used)
+    g.set_priors_var(cov)
+    o.set_priors_var(np.stack(cov[:4]), np.stack(cov[4:]))
+    g.update_all_beliefs(); o.update_all_beliefs()
+    for _ in range(12):
+        g.synchronous_iteration(robustify=True, local_relin=True)
+        o.synchronous_iteration(robustify=True, local_relin=True)
+    assert relerr(g.get_means(), np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])) < 1e-8
+    np.testing.assert_allclose(g.cam_nodes[3].mu, prob.cam_means[3], atol=1e-12)   # untouched keyframe = its prior
+    assert abs(g.are() - o.are()) < 1e-8 * o.are()
+    g.close()
+
+
+def test_error_behaviour():
+    from gbp_b200 import _lib as L
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.balio import BALProblem
+    G = load_golden("fr1desk_vsmall")
+    P = golden_problem(G)
+    cfg = golden_configs(G)
+    bad = BALProblem(P.cam_id.copy(), P.lmk_id.copy(), P.z, P.cam_means, P.lmk_means, P.K4)
+    bad.lmk_id[5] = P.n_points + 3
+    with pytest.raises(L.GbpError, match="landmark id"):
+        create_ba_graph(bad, cfg)
+    with pytest.raises(ValueError, match="unknown loss"):
+        create_ba_graph(P, dict(cfg, loss="tukey"))
+    g = create_ba_graph(P, cfg)
+    with pytest.raises(L.GbpError, match="priors not set"):
+        g.synchronous_iteration()
+    with pytest.raises(ValueError):
+        g.factors[0].eta_damping = 0.123
+    g.close()
