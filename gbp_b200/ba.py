@@ -536,6 +536,14 @@ class BAFactorGraph:
         sigma = np.linalg.inv(lam)
         return sigma @ eta, sigma
 
+    def reset(self):
+        """Engine extension: back to the state right after create_ba_graph."""
+        self._flush()
+        self._eng.reset()
+        for m in self._mirrors.values():
+            m.valid = False
+        self._res_cache = None
+
     def close(self):
         self._eng.close()
 

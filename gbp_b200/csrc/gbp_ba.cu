@@ -80,7 +80,7 @@ struct gbp_ba_graph {
     DevBuf<Tile> tiles;
     DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
-    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial;
+    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
@@ -92,7 +92,7 @@ struct gbp_ba_graph {
         z.release(); linpoint.release(); msg_cam.release(); msg_lmk.release(); sigma2a.release();
         cam_belief.release(); lmk_belief.release(); cam_prior.release(); lmk_prior.release(); cam_partial.release();
         tile_partial.release(); tile_metric.release(); metric_out.release(); edge_max.release();
-        tile_max.release(); cam_max.release();
+        tile_max.release(); cam_max.release(); cam_mu0.release(); lmk_mu0.release();
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -407,39 +407,39 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
     ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3); ALLOC(metric_out, 4);
     ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+    ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
 #undef ALLOC
 #define UP(buf, vec) if (!(vec).empty() && (e = cudaMemcpyAsync(g->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload " #buf)
     UP(tiles, tiles); UP(lmk_idx, h_lmk_idx); UP(z, h_z); UP(slot_of_factor, g->h_slot_of_factor);
     UP(lmk_ptr, h_lmk_ptr); UP(lmk_slots, h_lmk_slots); UP(cam_tile_ptr, h_cam_tile_ptr); UP(cam_tiles, h_cam_tiles);
 #undef UP
-#define ZERO(buf) if ((e = cudaMemsetAsync(g->buf.p, 0, std::max<size_t>(g->buf.bytes(), 1), g->stream)) != cudaSuccess) return bail(e, "memset " #buf)
+    if (C > 0 && (e = cudaMemcpyAsync(g->cam_mu0.p, cam_mu0, (size_t)C * 48, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload cam_mu0");
+    if (L > 0 && (e = cudaMemcpyAsync(g->lmk_mu0.p, lmk_mu0, (size_t)L * 24, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload lmk_mu0");
+    {
+        int rc = gbp_ba_reset(g);
+        if (rc != GBP_OK) { delete g; return rc; }
+    }
+    *out = g;
+    return GBP_OK;
+}
+
+int gbp_ba_reset(gbp_handle h) {
+    CHECK_H(h);
+    gbp_ba_graph* g = h;
+#define ZERO(buf) CU(cudaMemsetAsync(g->buf.p, 0, std::max<size_t>(g->buf.bytes(), 1), g->stream))
     ZERO(msg_cam); ZERO(msg_lmk); ZERO(cam_prior); ZERO(lmk_prior); ZERO(cam_partial); ZERO(tile_partial);
     ZERO(edge_max); ZERO(tile_max); ZERO(cam_max);
 #undef ZERO
     // beliefs: eta = Lambda = 0, mu = initial means; edges linearised at those means
-    {
-        DevBuf<double> tmp;
-        const size_t nmu = std::max((size_t)C * 6, (size_t)L * 3);
-        if ((e = tmp.alloc(nmu)) != cudaSuccess) return bail(e, "cudaMalloc staging");
-        if (C > 0) {
-            cudaMemcpyAsync(tmp.p, cam_mu0, (size_t)C * 6 * 8, cudaMemcpyHostToDevice, g->stream);
-            init_belief_kernel<<<(C + 127) / 128, 128, 0, g->stream>>>(tmp.p, C, 6, CAM_B, g->cam_belief.p);
-            cudaStreamSynchronize(g->stream);
-        }
-        if (L > 0) {
-            cudaMemcpyAsync(tmp.p, lmk_mu0, (size_t)L * 3 * 8, cudaMemcpyHostToDevice, g->stream);
-            init_belief_kernel<<<(L + 127) / 128, 128, 0, g->stream>>>(tmp.p, L, 3, LMK_B, g->lmk_belief.p);
-            cudaStreamSynchronize(g->stream);
-        }
-        tmp.release();
-    }
+    if (g->C > 0) init_belief_kernel<<<(g->C + 127) / 128, 128, 0, g->stream>>>(g->cam_mu0.p, g->C, 6, CAM_B, g->cam_belief.p);
+    if (g->L > 0) init_belief_kernel<<<(g->L + 127) / 128, 128, 0, g->stream>>>(g->lmk_mu0.p, g->L, 3, LMK_B, g->lmk_belief.p);
+    CU(cudaGetLastError());
     if (g->n_tiles > 0) {
         int rc = DISPATCH_T(g, launch_init_t);
-        if (rc != GBP_OK) { delete g; return rc; }
+        if (rc != GBP_OK) return rc;
     }
-    if ((e = cudaStreamSynchronize(g->stream)) != cudaSuccess) return bail(e, "graph initialisation");
-    if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "graph initialisation kernels");
-    *out = g;
+    CU(cudaStreamSynchronize(g->stream));
+    g->priors_set = false;
     return GBP_OK;
 }
 

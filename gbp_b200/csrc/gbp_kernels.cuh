@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
     coop_copy<T>(s_mc, p.msg_cam + base * CAM_M, n * CAM_M);
     coop_copy<T>(s_ml, p.msg_lmk + base * LMK_M, n * LMK_M);
     coop_copy<T>(s_lp, p.linpoint + base * 9, n * 9);
-    if (tid < CAM_B) s_cb[tid] = p.cam_belief[(long long)tl.cam * CAM_B + tid];
+    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
     __syncthreads();
 
     bool relin = false;

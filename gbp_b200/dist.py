@@ -1,0 +1,198 @@
+"""Multi-GPU GBP sweep: the factor graph is cut by LANDMARK across the ranks of one box.
+
+Every factor lives with its landmark, so all landmarks are interior (their incoming messages
+are local) and the boundary variables are the keyframes, replicated on every rank.  Per
+synchronous iteration each rank runs the sweep over its own edges, reduces its local
+factor->keyframe messages to one partial (eta, Lambda) sum per keyframe (C x 27 doubles), and the
+ranks exchange those partial sums with ONE all-gather (NCCL over NVLink / NVSwitch; gloo in the
+CPU tests); every rank then adds prior + the partials in rank order, so the keyframe beliefs are
+bit-identical everywhere.  ARE / energy need a 3-scalar all-reduce only when the client asks.
+
+The reference has no distributed code; this is new functionality behind the same
+`synchronous_iteration` surface.
+
+The compute engine is injectable (`engine_factory`) so that the partition / exchange / merge logic
+is testable on CPU with world_size 2 (tests/test_dist_cpu.py); the product always uses the CUDA
+engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .balio import BALProblem
+
+
+def landmark_partition(n_lmks: int, world: int):
+    """Contiguous landmark blocks: rank r owns [bounds[r], bounds[r+1])."""
+    return [(n_lmks * r) // world for r in range(world + 1)]
+
+
+def local_problem(prob: BALProblem, rank: int, world: int):
+    """The sub-problem of one rank: all keyframes, its landmark block, the measurements of those landmarks
+    (file order preserved).  Returns (BALProblem with local landmark ids, global index of each local measurement)."""
+    b = landmark_partition(prob.n_points, world)
+    l0, l1 = b[rank], b[rank + 1]
+    sel = np.nonzero((prob.lmk_id >= l0) & (prob.lmk_id < l1))[0]
+    sub = BALProblem(prob.cam_id[sel], prob.lmk_id[sel] - l0, prob.z[sel], prob.cam_means, prob.lmk_means[l0:l1], prob.K4)
+    return sub, sel, (l0, l1)
+
+
+class _DevArray:
+    """Zero-copy view of engine-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class CudaEngineAdapter:
+    """The CUDA engine seen through the four operations the exchange layer needs."""
+
+    def __init__(self, sub: BALProblem, configs, device, stream, **kw):
+        import torch
+        from .engine import BAEngine
+        self.eng = BAEngine(sub.cam_id, sub.lmk_id, sub.z, sub.cam_means, sub.lmk_means, sub.K4, configs, device=device,
+                            stream=stream, **kw)
+        ptr, nbytes = self.eng.device_ptr(L.F_CAM_PARTIAL)
+        self._partial = torch.as_tensor(_DevArray(ptr, nbytes // 8), device=f"cuda:{device}")
+        self._torch = torch
+
+    C = property(lambda self: self.eng.C)
+    L = property(lambda self: self.eng.L)
+    F = property(lambda self: self.eng.F)
+
+    def prior_scan(self):
+        return self._torch.from_numpy(self.eng.prior_scan())
+
+    def generate_priors(self, weaker, cam_max):
+        self.eng.generate_priors(weaker, cam_max.cpu().numpy())
+
+    def scale_priors(self, f):
+        self.eng.scale_priors(f)
+
+    def sweep_local(self, stages):
+        self.eng.sweep_local(stages)
+
+    def partial_tensor(self):
+        return self._partial
+
+    def new_gather_buffer(self, world):
+        return self._torch.empty(world * self._partial.numel(), dtype=self._torch.float64, device=self._partial.device)
+
+    def apply_gathered(self, gathered, world):
+        self.eng.cam_update(gathered.data_ptr(), world)
+
+    def iterate_single(self, robustify, local_relin):
+        self.eng.iterate(1, robustify=robustify, local_relin=local_relin)
+
+    def update_beliefs_single(self):
+        self.eng.update_beliefs()
+
+    def metrics(self):
+        a, e, n = self.eng.metrics()
+        return np.array([a, e, float(n)])
+
+    def cam_means(self):
+        return self.eng.read(L.F_CAM_BELIEF)[:, 27:]
+
+    def lmk_means(self):
+        return self.eng.read(L.F_LMK_BELIEF)[:, 9:]
+
+    def fill_iters(self, v):
+        self.eng.fill_iters(v)
+
+    def close(self):
+        self.eng.close()
+
+
+class PartitionedBAGraph:
+    """`synchronous_iteration` / `generate_priors_var` / `are` / `energy` over a landmark-partitioned graph."""
+
+    def __init__(self, prob: BALProblem, configs, rank=0, world=1, device=0, stream=None, dist=None,
+                 engine_factory=None, **engine_kw):
+        if world > 1 and dist is None:
+            raise ValueError("world > 1 needs an initialised torch.distributed module")
+        self.rank, self.world, self.dist = rank, world, dist
+        self.F_total, self.L_total, self.C = prob.n_edges, prob.n_points, prob.n_keyframes
+        sub, self.local_measurements, self.lmk_range = local_problem(prob, rank, world)
+        factory = engine_factory or (lambda s, c: CudaEngineAdapter(s, c, device, stream, **engine_kw))
+        self.adapter = factory(sub, configs)
+        self._gather = self.adapter.new_gather_buffer(world) if world > 1 else None
+
+    @property
+    def engine(self):
+        return self.adapter.eng
+
+    # ------------------------------------------------------------------ exchange
+    def _exchange_and_update(self):
+        a = self.adapter
+        self.dist.all_gather_into_tensor(self._gather, a.partial_tensor())
+        a.apply_gathered(self._gather, self.world)
+
+    # ------------------------------------------------------------------ API
+    def generate_priors_var(self, weaker_factor=100):
+        """gbp/gbp_ba.py:20-34 with the per-keyframe maximum taken over all ranks."""
+        a = self.adapter
+        if self.world == 1:
+            a.generate_priors(weaker_factor, a.prior_scan())
+            return
+        cam_max = a.prior_scan()
+        dev = self._gather.device
+        t = cam_max.to(dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        a.generate_priors(weaker_factor, t.cpu())
+
+    def weaken_priors(self, f):
+        self.adapter.scale_priors(f)
+
+    def update_all_beliefs(self):
+        if self.world == 1:
+            self.adapter.update_beliefs_single()
+        else:
+            self.adapter.sweep_local(L.ST_BELIEFS)
+            self._exchange_and_update()
+
+    def synchronous_iteration(self, local_relin=True, robustify=False):
+        """gbp/gbp.py:86-92 over the partitioned graph: local sweep -> one all-gather -> keyframe beliefs."""
+        if self.world == 1:
+            self.adapter.iterate_single(robustify, local_relin)
+            return
+        st = L.ST_MESSAGES | L.ST_BELIEFS
+        if robustify:
+            st |= L.ST_ROBUSTIFY
+        if local_relin:
+            st |= L.ST_RELIN | L.ST_LOCAL_DAMPING
+        self.adapter.sweep_local(st)
+        self._exchange_and_update()
+
+    def fill_iters(self, value):
+        self.adapter.fill_iters(value)
+
+    def metrics(self):
+        """(ARE, energy, number of factors with iters_since_relin == 0) over the WHOLE graph."""
+        m = self.adapter.metrics()
+        if self.world > 1:
+            import torch
+            t = torch.from_numpy(m).to(self._gather.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            m = t.cpu().numpy()
+        return float(m[0]) / self.F_total, float(m[1]), int(round(float(m[2])))
+
+    def are(self):
+        return self.metrics()[0]
+
+    def energy(self):
+        return self.metrics()[1]
+
+    def get_means(self):
+        """All belief means in variable order (keyframes, then landmarks) on every rank."""
+        cam = self.adapter.cam_means().ravel()
+        lmk = self.adapter.lmk_means()
+        if self.world > 1:
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, lmk)
+            lmk = np.concatenate(parts, axis=0)
+        return np.concatenate([cam, lmk.ravel()])
+
+    def close(self):
+        self.adapter.close()

@@ -75,6 +75,9 @@ class BAEngine:
         except Exception:
             pass
 
+    def reset(self):
+        L.check(self._lib.gbp_ba_reset(self._h))
+
     # ------------------------------------------------------------------ priors
     def prior_scan(self):
         out = np.zeros(self.C)

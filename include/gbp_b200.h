@@ -104,6 +104,9 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F,
                   const double* cam_mu0 /* C x 6 */, const double* lmk_mu0 /* L x 3 */,
                   const double K[4] /* fx fy cx cy */, int device, void* stream, gbp_handle* out);
 int gbp_ba_destroy(gbp_handle h);
+/* Back to the state right after gbp_ba_create (zero messages and priors, initial means and
+ * linearisation points, iters_since_relin = 1): re-run a solve without rebuilding the graph. */
+int gbp_ba_reset(gbp_handle h);
 
 /* Sizes: C, L, F, number of edge tiles, edges per tile, padded edge slots. */
 int gbp_ba_sizes(gbp_handle h, int64_t out[6]);

@@ -1,0 +1,170 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: landmark partition, the one all-gather of
+keyframe partial sums per iteration, rank-ordered merge, cross-rank prior maxima and metric sums.
+The compute engine is replaced by an oracle-backed stand-in (the CUDA engine needs a GPU); what is
+under test is gbp_b200/dist.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, relerr
+
+CFG = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8,
+           eta_damping=0.4, prior_std_weaker_factor=50.0)
+IU6, IU3 = np.triu_indices(6), np.triu_indices(3)
+
+
+class OracleAdapter:
+    """Same interface as gbp_b200.dist.CudaEngineAdapter, arithmetic by the NumPy oracle."""
+
+    def __init__(self, sub, cfg):
+        from oracle.gbp_oracle import BAOracle
+        self.o = BAOracle(sub.cam_id, sub.lmk_id, sub.z, sub.cam_means, sub.lmk_means, sub.K4, cfg)
+        self.C, self.L, self.F = self.o.C, self.o.L, self.o.F
+        self._partial = torch.zeros(self.C * 27, dtype=torch.float64)
+
+    def prior_scan(self):
+        o = self.o
+        self._fmax = o.factor_lam.reshape(o.F, -1).max(axis=1)
+        cmax = np.zeros(o.C); np.maximum.at(cmax, o.cam, self._fmax)
+        return torch.from_numpy(cmax)
+
+    def generate_priors(self, weaker, cam_max):
+        o = self.o
+        lmax = np.zeros(o.L); np.maximum.at(lmax, o.lmk, self._fmax)
+        o.cam_prior_lam = np.eye(6)[None] * (cam_max.numpy() / weaker ** 2)[:, None, None]
+        o.lmk_prior_lam = np.eye(3)[None] * (lmax / weaker ** 2)[:, None, None]
+        o.cam_prior_eta = np.einsum("vij,vj->vi", o.cam_prior_lam, o.cam_mu)
+        o.lmk_prior_eta = np.einsum("vij,vj->vi", o.lmk_prior_lam, o.lmk_mu)
+
+    def scale_priors(self, f):
+        self.o.weaken_priors(f)
+
+    def sweep_local(self, stages):
+        from gbp_b200 import _lib as L
+        o = self.o
+        if stages & L.ST_ROBUSTIFY:
+            o.robustify_all_factors()
+        if stages & L.ST_RELIN:
+            o.relinearise_factors()
+        if stages & L.ST_MESSAGES:
+            o.compute_all_messages(local_relin=bool(stages & L.ST_LOCAL_DAMPING))
+        if stages & L.ST_BELIEFS:
+            ce = np.zeros((o.C, 6)); cl = np.zeros((o.C, 6, 6))
+            np.add.at(ce, o.cam, o.msg_cam_eta); np.add.at(cl, o.cam, o.msg_cam_lam)
+            self._partial.copy_(torch.from_numpy(np.concatenate([ce, cl[:, IU6[0], IU6[1]]], axis=1).ravel()))
+            le = o.lmk_prior_eta.copy(); ll = o.lmk_prior_lam.copy()
+            np.add.at(le, o.lmk, o.msg_lmk_eta); np.add.at(ll, o.lmk, o.msg_lmk_lam)
+            o.lmk_eta, o.lmk_lam = le, ll
+            o.lmk_mu = np.einsum("vij,vj->vi", np.linalg.inv(ll), le)
+
+    def partial_tensor(self):
+        return self._partial
+
+    def new_gather_buffer(self, world):
+        return torch.empty(world * self._partial.numel(), dtype=torch.float64)
+
+    def apply_gathered(self, gathered, world):
+        o = self.o
+        parts = gathered.numpy().reshape(world, o.C, 27)
+        ce = o.cam_prior_eta.copy(); cl = o.cam_prior_lam.copy()
+        for r in range(world):
+            ce += parts[r, :, :6]
+            full = np.zeros((o.C, 6, 6))
+            full[:, IU6[0], IU6[1]] = parts[r, :, 6:]
+            full[:, IU6[1], IU6[0]] = parts[r, :, 6:]
+            cl += full
+        o.cam_eta, o.cam_lam = ce, cl
+        o.cam_mu = np.einsum("vij,vj->vi", np.linalg.inv(cl), ce)
+
+    def metrics(self):
+        o = self.o
+        r = o.compute_residuals()
+        nr = np.linalg.norm(r, axis=1)
+        return np.array([nr.sum(), float(np.sum(0.5 * nr ** 2 / o.adaptive_var)), float(o.n_relinearising())])
+
+    def cam_means(self):
+        return self.o.cam_mu
+
+    def lmk_means(self):
+        return self.o.lmk_mu
+
+    def fill_iters(self, v):
+        self.o.iters_since_relin[:] = v
+
+    def close(self):
+        pass
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gbp_b200.dist import PartitionedBAGraph
+    from gbp_b200.synthetic import make_synthetic
+    prob = make_synthetic(12, 600, 6, seed=3)
+    pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, dist=dist, engine_factory=lambda s, c: OracleAdapter(s, c))
+    pg.generate_priors_var(50.0)
+    pg.update_all_beliefs()
+    trace = []
+    for i in range(20):
+        if i in (3, 8):
+            pg.fill_iters(1)
+        trace.append(pg.metrics())
+        pg.synchronous_iteration(robustify=True, local_relin=True)
+    trace.append(pg.metrics())
+    means = pg.get_means()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=means, trace=np.array(trace), n_local=pg.adapter.F,
+             lmk_range=np.array(pg.lmk_range))
+    dist.destroy_process_group()
+
+
+def test_landmark_partition_covers_everything():
+    from gbp_b200.dist import landmark_partition, local_problem
+    from gbp_b200.synthetic import make_synthetic
+    prob = make_synthetic(8, 101, 5, seed=1)
+    for world in (1, 2, 3, 8):
+        b = landmark_partition(prob.n_points, world)
+        assert b[0] == 0 and b[-1] == prob.n_points and all(x <= y for x, y in zip(b, b[1:]))
+        seen = np.zeros(prob.n_edges, dtype=int)
+        for r in range(world):
+            sub, sel, (l0, l1) = local_problem(prob, r, world)
+            seen[sel] += 1
+            assert sub.n_keyframes == prob.n_keyframes and sub.n_points == l1 - l0
+            assert sub.lmk_id.min(initial=0) >= 0 and sub.lmk_id.max(initial=-1) < max(l1 - l0, 1)
+            assert np.array_equal(sub.lmk_means, prob.lmk_means[l0:l1])
+            assert np.all(np.diff(sel) > 0)           # file order preserved
+        assert np.all(seen == 1)
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    from oracle.gbp_oracle import BAOracle
+    from gbp_b200.synthetic import make_synthetic
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    # every rank sees the same global state
+    assert np.array_equal(r0["means"], r1["means"]) and np.array_equal(r0["trace"], r1["trace"])
+    prob = make_synthetic(12, 600, 6, seed=3)
+    assert int(r0["n_local"]) + int(r1["n_local"]) == prob.n_edges and r0["lmk_range"][1] == r1["lmk_range"][0]
+    # and it equals the unpartitioned graph
+    o = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
+    o.generate_priors_var(50.0); o.update_all_beliefs()
+    trace = []
+    for i in range(20):
+        if i in (3, 8):
+            o.iters_since_relin[:] = 1
+        trace.append((o.are(), o.energy(), o.n_relinearising()))
+        o.synchronous_iteration(robustify=True, local_relin=True)
+    trace.append((o.are(), o.energy(), o.n_relinearising()))
+    trace = np.array(trace)
+    assert np.array_equal(trace[:, 2], r0["trace"][:, 2])
+    assert relerr(r0["trace"][:, :2], trace[:, :2]) < 1e-9
+    assert relerr(r0["means"], np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])) < 1e-9
