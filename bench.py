@@ -141,7 +141,12 @@ def bench_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream shared by torch (events, NCCL ordering, L2 flush) and the engine:
+    # the default stream's handle is 0, which the C ABI reads as "create your own stream"
+    work_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+    assert stream != 0
     hbm_peak, peak_src = peaks()
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 

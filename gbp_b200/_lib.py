@@ -46,7 +46,7 @@ class GbpError(RuntimeError):
 class GbpConfig(C.Structure):
     _fields_ = [("gauss_noise_std", C.c_double), ("eta_damping", C.c_double), ("beta", C.c_double),
                 ("Nstds", C.c_double), ("num_undamped_iters", C.c_int32), ("min_linear_iters", C.c_int32),
-                ("loss", C.c_int32), ("tile_edges", C.c_int32), ("lmk_block", C.c_int32), ("reserved", C.c_int32)]
+                ("loss", C.c_int32), ("tile_edges", C.c_int32), ("lmk_block", C.c_int32), ("kernel_variant", C.c_int32)]
 
 
 EXPORTS = [

@@ -296,7 +296,8 @@ _BELIEF_FIELDS = (L.F_CAM_BELIEF, L.F_LMK_BELIEF)
 class BAFactorGraph:
     """gbp/gbp_ba.py:12-69 on top of gbp/gbp.py:11-153, device resident."""
 
-    def __init__(self, problem: balio.BALProblem, configs: dict, device=0, stream=None, tile_edges=0, lmk_block=0):
+    def __init__(self, problem: balio.BALProblem, configs: dict, device=0, stream=None, tile_edges=0, lmk_block=0,
+                 kernel_variant=0):
         self.nonlinear_factors = True
         self._eta_damping = float(configs["eta_damping"])
         self._beta = float(configs["beta"])
@@ -308,7 +309,7 @@ class BAFactorGraph:
         self.K = problem.K
         self._eng = BAEngine(problem.cam_id, problem.lmk_id, problem.z, problem.cam_means, problem.lmk_means,
                              problem.K4, configs, device=device, stream=stream, tile_edges=tile_edges,
-                             lmk_block=lmk_block)
+                             lmk_block=lmk_block, kernel_variant=kernel_variant)
         e = self._eng
         self.cam_nodes = _LazySeq(e.C, lambda i: FrameVariableNode(self, i))
         self.lmk_nodes = _LazySeq(e.L, lambda i: LandmarkVariableNode(self, i))
@@ -548,7 +549,8 @@ class BAFactorGraph:
         self._eng.close()
 
 
-def create_ba_graph(bal_file, configs, device=0, stream=None, tile_edges=0, lmk_block=0):
+def create_ba_graph(bal_file, configs, device=0, stream=None, tile_edges=0, lmk_block=0, kernel_variant=0):
     """gbp/gbp_ba.py:97-150: build the graph object from a BAL-style file (text or .npz)."""
     problem = bal_file if isinstance(bal_file, balio.BALProblem) else balio.read_bal(bal_file)
-    return BAFactorGraph(problem, configs, device=device, stream=stream, tile_edges=tile_edges, lmk_block=lmk_block)
+    return BAFactorGraph(problem, configs, device=device, stream=stream, tile_edges=tile_edges, lmk_block=lmk_block,
+                         kernel_variant=kernel_variant)

@@ -117,10 +117,16 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
     const SweepParams p = sweep_params(g, stages);
     constexpr size_t smem = sweep_smem_bytes<T>();
     static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
-    if (g->robust)
+    if (g->cfg.kernel_variant == 1) {   // first-version kernel (cooperative LDG/STS staging), for A/B measurements
+        if (g->robust)
+            sweep_kernel_ldg<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
+        else
+            sweep_kernel_ldg<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    } else if (g->robust) {
         sweep_kernel<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
-    else
+    } else {
         sweep_kernel<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    }
     g->launches++;
     CU(cudaGetLastError());
     return GBP_OK;

@@ -62,18 +62,259 @@ __device__ __forceinline__ void coop_copy(double* __restrict__ dst, const double
 }
 
 // ----------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier primitives, sm_90+ PTX.  The tile's contiguous row blocks
+// are moved global <-> shared by the copy engine (SASS: UBLKCP), no registers, no LSU issue.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "GBP_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra GBP_DONE;\n\t"
+        "bra GBP_WAIT;\n\t"
+        "GBP_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-edge register inputs fetched straight from global memory
+struct EdgeRegs {
+    int it, fl;
+    double z[2];
+    double bl[LMK_B];   // landmark belief row (gathered)
+};
+
+__device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e, EdgeRegs& r) {
+    const int lmk = p.lmk_idx[e];
+    r.it = p.iters[e];
+    r.fl = p.flags[e];
+    const double2 zz = reinterpret_cast<const double2*>(p.z)[e];
+    r.z[0] = zz.x;
+    r.z[1] = zz.y;
+    const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
+#pragma unroll
+    for (int k = 0; k < LMK_B / 2; ++k) {
+        const double2 v = __ldg(src + k);
+        r.bl[2 * k] = v.x;
+        r.bl[2 * k + 1] = v.y;
+    }
+}
+
+// robustify -> relinearise -> messages for ONE edge.  my_* are the edge's rows in shared memory
+// (read, then overwritten in place with the new messages / linearisation point); s_cb is the
+// keyframe belief row shared by the whole tile.  Returns true when the edge relinearised.
+template <bool ROBUST>
+__device__ __forceinline__ bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const double* s_cb, double* my_lp,
+                                           double* my_mc, double* my_ml) {
+    const double* z = r.z;
+    const double* bl = r.bl;
+    int it = r.it, fl = r.fl;
+    bool relin = false;
+    double x0[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x0[k] = my_lp[k];
+
+    // --- relinearisation test (gbp/gbp.py:72-75): |linpoint - [mu_cam, mu_lmk]| > beta
+    if (p.stages & ST_RELIN) {
+        double d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double d = x0[k] - s_cb[27 + k];
+            d2 += d * d;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double d = x0[6 + k] - bl[9 + k];
+            d2 += d * d;
+        }
+        relin = (sqrt(d2) > p.beta) && (it >= p.min_linear);
+    }
+
+    double var = p.var0;
+    double J[18], h0[2];
+    bool lin_done = false;
+    if (ROBUST) {
+        var = p.sigma2a[e];
+        if (p.stages & ST_ROBUSTIFY) {
+            // robustify_loss uses h at the STORED linearisation point (gbp/gbp.py:309-312)
+            double r0, r1;
+            if (relin) {
+                double hold[2];
+                meas_fn(p.K, x0, hold);
+                r0 = z[0] - hold[0];
+                r1 = z[1] - hold[1];
+            } else {
+                linearise(p.K, x0, J, h0);
+                lin_done = true;
+                r0 = z[0] - h0[0];
+                r1 = z[1] - h0[1];
+            }
+            bool rf;
+            var = robust_variance(p.loss, p.var0, p.nstds, r0, r1, &rf);
+            fl = rf ? (fl | 2) : (fl & ~2);
+            p.sigma2a[e] = var;
+        }
+    }
+
+    if (p.stages & ST_RELIN) {
+        if (relin) {   // gbp/gbp.py:76-78
+#pragma unroll
+            for (int k = 0; k < 6; ++k) x0[k] = s_cb[27 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x0[6 + k] = bl[9 + k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];
+            it = 0;
+            fl &= ~1;
+            lin_done = false;
+        } else {
+            it += 1;   // gbp/gbp.py:80
+        }
+    }
+
+    if (p.stages & ST_MESSAGES) {
+        if (!lin_done) linearise(p.K, x0, J, h0);
+        double b[2];
+        factor_rhs(J, x0, z, h0, b);
+        double damping = p.eta_damping;
+        if (p.stages & ST_LOCAL_DAMPING) {   // gbp/gbp.py:49-52
+            if (it == p.num_undamped) fl |= 1;
+            damping = (fl & 1) ? p.eta_damping : 0.0;
+        }
+        // message to the landmark: marginalise the keyframe (6x6 Cholesky)
+        double nl_eta[3], nl_lam[6];
+        {
+            double P[21], ev[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ev[k] = s_cb[k] - my_mc[k];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
+            message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
+        }
+        // message to the keyframe: marginalise the landmark (3x3 Cholesky); written in place
+        {
+            double P[6], ev[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ev[k] = bl[k] - my_ml[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) P[k] = bl[3 + k] - my_ml[3 + k];
+            message<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) my_ml[k] = nl_eta[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) my_ml[3 + k] = nl_lam[k];
+    }
+    p.iters[e] = it;
+    p.flags[e] = fl;
+    return relin;
+}
+
+// column sums of the tile's (new) messages to its keyframe -> tile_partial[tile][27]
+template <int T>
+__device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile, int n, const double* s_mc, double* s_red) {
+    constexpr int G = T / 32;
+    const int tid = threadIdx.x;
+    if (tid < CAM_M * G) {
+        const int col = tid % CAM_M, g = tid / CAM_M;
+        const int r1 = min(n, (g + 1) * 32);
+        double acc = 0.0;
+        for (int r = g * 32; r < r1; ++r) acc += s_mc[r * CAM_M + col];
+        s_red[g * CAM_M + col] = acc;
+    }
+    __syncthreads();
+    if (tid < CAM_M) {
+        double acc = s_red[tid];
+#pragma unroll
+        for (int g = 1; g < G; ++g) acc += s_red[g * CAM_M + tid];
+        p.tile_partial[(long long)tile * CAM_M + tid] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K1-K3 (+ the keyframe half of K4): robustify -> relinearise -> factor-to-variable messages
 // -> per-tile sum of the messages to the keyframe.   One CTA per tile, one thread per edge.
 // Replaces gbp/gbp.py:82-84,296-332 / 64-80,267-294 / 46-54,334-373 for reprojection factors.
+//
+// sweep_kernel      : tile rows staged by TMA bulk copies (one elected thread, mbarrier
+//                     completion); every thread issues its gathers (landmark index -> 96 B belief
+//                     row) BEFORE waiting, so all of a tile's DRAM round trips overlap; new rows
+//                     leave by bulk stores.
+// sweep_kernel_ldg  : first version (cooperative LDG/STS copies), kept for A/B measurements.
 // ----------------------------------------------------------------------------------------
 template <int T, bool ROBUST>
 __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     double* s_mc = smem;                 // [T][27]
     double* s_ml = s_mc + T * CAM_M;     // [T][9]
     double* s_lp = s_ml + T * LMK_M;     // [T][9]
     double* s_cb = s_lp + T * 9;         // [33] keyframe belief (+pad to 34)
     double* s_red = s_cb + 34;           // [T/32][27]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    const Tile tl = p.tiles[tile];
+    const int n = tl.count;
+    const int n_even = (n + 1) & ~1;     // bulk copies move multiples of 16 B; the extra row is tile padding
+    const long long base = (long long)tile * T;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)n_even * (CAM_M + LMK_M + 9) * 8);
+        bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
+        bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
+        bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
+    }
+    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
+    EdgeRegs r;
+    if (tid < n) load_edge_regs(p, base + tid, r);
+    __syncthreads();          // s_cb visible
+    mbar_wait(bar, 0);        // bulk loads landed
+
+    bool relin = false;
+    if (tid < n) relin = edge_sweep<ROBUST>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
+    fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
+    const int any_relin = __syncthreads_or(relin ? 1 : 0);
+
+    if (tid == 0) {
+        if (p.stages & ST_MESSAGES) {
+            bulk_s2g(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8);
+            bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+        }
+        if (any_relin) bulk_s2g(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72);
+        bulk_commit();
+    }
+    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
+    if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
+}
+
+template <int T, bool ROBUST>
+__global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
+    extern __shared__ __align__(128) double smem[];
+    double* s_mc = smem;
+    double* s_ml = s_mc + T * CAM_M;
+    double* s_lp = s_ml + T * LMK_M;
+    double* s_cb = s_lp + T * 9;
+    double* s_red = s_cb + 34;
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
@@ -84,127 +325,14 @@ __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
     coop_copy<T>(s_mc, p.msg_cam + base * CAM_M, n * CAM_M);
     coop_copy<T>(s_ml, p.msg_lmk + base * LMK_M, n * LMK_M);
     coop_copy<T>(s_lp, p.linpoint + base * 9, n * 9);
-    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
+    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
     __syncthreads();
 
     bool relin = false;
     if (tid < n) {
-        const long long e = base + tid;
-        const int lmk = p.lmk_idx[e];
-        int it = p.iters[e];
-        int fl = p.flags[e];
-        const double2 zz = reinterpret_cast<const double2*>(p.z)[e];
-        const double z[2] = {zz.x, zz.y};
-        double bl[LMK_B];
-        {
-            const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
-#pragma unroll
-            for (int k = 0; k < LMK_B / 2; ++k) {
-                const double2 v = __ldg(src + k);
-                bl[2 * k] = v.x;
-                bl[2 * k + 1] = v.y;
-            }
-        }
-        double* my_lp = s_lp + tid * 9;
-        double* my_mc = s_mc + tid * CAM_M;
-        double* my_ml = s_ml + tid * LMK_M;
-        double x0[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) x0[k] = my_lp[k];
-
-        // --- relinearisation test (gbp/gbp.py:72-75): |linpoint - [mu_cam, mu_lmk]| > beta
-        if (p.stages & ST_RELIN) {
-            double d2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const double d = x0[k] - s_cb[27 + k];
-                d2 += d * d;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double d = x0[6 + k] - bl[9 + k];
-                d2 += d * d;
-            }
-            relin = (sqrt(d2) > p.beta) && (it >= p.min_linear);
-        }
-
-        double var = p.var0;
-        double J[18], h0[2];
-        bool lin_done = false;
-        if (ROBUST) {
-            var = p.sigma2a[e];
-            if (p.stages & ST_ROBUSTIFY) {
-                // robustify_loss uses h at the STORED linearisation point (gbp/gbp.py:309-312)
-                double r0, r1;
-                if (relin) {
-                    double hold[2];
-                    meas_fn(p.K, x0, hold);
-                    r0 = z[0] - hold[0];
-                    r1 = z[1] - hold[1];
-                } else {
-                    linearise(p.K, x0, J, h0);
-                    lin_done = true;
-                    r0 = z[0] - h0[0];
-                    r1 = z[1] - h0[1];
-                }
-                bool rf;
-                var = robust_variance(p.loss, p.var0, p.nstds, r0, r1, &rf);
-                fl = rf ? (fl | 2) : (fl & ~2);
-                p.sigma2a[e] = var;
-            }
-        }
-
-        if (p.stages & ST_RELIN) {
-            if (relin) {   // gbp/gbp.py:76-78
-#pragma unroll
-                for (int k = 0; k < 6; ++k) x0[k] = s_cb[27 + k];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) x0[6 + k] = bl[9 + k];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];
-                it = 0;
-                fl &= ~1;
-                lin_done = false;
-            } else {
-                it += 1;   // gbp/gbp.py:80
-            }
-        }
-
-        if (p.stages & ST_MESSAGES) {
-            if (!lin_done) linearise(p.K, x0, J, h0);
-            double b[2];
-            factor_rhs(J, x0, z, h0, b);
-            double damping = p.eta_damping;
-            if (p.stages & ST_LOCAL_DAMPING) {   // gbp/gbp.py:49-52
-                if (it == p.num_undamped) fl |= 1;
-                damping = (fl & 1) ? p.eta_damping : 0.0;
-            }
-            // message to the landmark: marginalise the keyframe (6x6 Cholesky)
-            double nl_eta[3], nl_lam[6];
-            {
-                double P[21], ev[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) ev[k] = s_cb[k] - my_mc[k];
-#pragma unroll
-                for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
-                message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
-            }
-            // message to the keyframe: marginalise the landmark (3x3 Cholesky); written in place
-            {
-                double P[6], ev[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) ev[k] = bl[k] - my_ml[k];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) P[k] = bl[3 + k] - my_ml[3 + k];
-                message<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) my_ml[k] = nl_eta[k];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) my_ml[3 + k] = nl_lam[k];
-        }
-        p.iters[e] = it;
-        p.flags[e] = fl;
+        EdgeRegs r;
+        load_edge_regs(p, base + tid, r);
+        relin = edge_sweep<ROBUST>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
     }
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
@@ -213,30 +341,12 @@ __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
         coop_copy<T>(p.msg_lmk + base * LMK_M, s_ml, n * LMK_M);
     }
     if (any_relin) coop_copy<T>(p.linpoint + base * 9, s_lp, n * 9);
-
-    if (p.stages & ST_BELIEFS) {
-        // column sums of the tile's messages to its keyframe
-        constexpr int G = T / 32;
-        if (tid < CAM_M * G) {
-            const int col = tid % CAM_M, g = tid / CAM_M;
-            const int r1 = min(n, (g + 1) * 32);
-            double acc = 0.0;
-            for (int r = g * 32; r < r1; ++r) acc += s_mc[r * CAM_M + col];
-            s_red[g * CAM_M + col] = acc;
-        }
-        __syncthreads();
-        if (tid < CAM_M) {
-            double acc = s_red[tid];
-#pragma unroll
-            for (int g = 1; g < G; ++g) acc += s_red[g * CAM_M + tid];
-            p.tile_partial[(long long)tile * CAM_M + tid] = acc;
-        }
-    }
+    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
 }
 
 template <int T>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(double) * (size_t)(T * (CAM_M + LMK_M + 9) + 34 + (T / 32) * CAM_M);
+    return sizeof(double) * (size_t)(T * (CAM_M + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
 }
 
 // ----------------------------------------------------------------------------------------

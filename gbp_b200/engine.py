@@ -33,7 +33,7 @@ def pack_sym(full):
 
 class BAEngine:
     def __init__(self, cam_id, lmk_id, z, cam_mu0, lmk_mu0, K4, configs, device=0, stream=None,
-                 tile_edges=0, lmk_block=0):
+                 tile_edges=0, lmk_block=0, kernel_variant=0):
         lib = L.load()
         self._lib = lib
         self._h = None
@@ -50,7 +50,7 @@ class BAEngine:
             raise ValueError(f"unknown loss {loss!r} (None, 'huber' or 'constant')")
         cfg = L.GbpConfig(float(configs["gauss_noise_std"]), float(configs["eta_damping"]), float(configs["beta"]),
                           float(configs.get("Nstds", 3.0)), int(configs["num_undamped_iters"]),
-                          int(configs["min_linear_iters"]), L.LOSS_CODES[loss], int(tile_edges), int(lmk_block), 0)
+                          int(configs["min_linear_iters"]), L.LOSS_CODES[loss], int(tile_edges), int(lmk_block), int(kernel_variant))
         self.cfg = cfg
         h = C.c_void_p()
         L.check(lib.gbp_ba_create(C.byref(cfg), len(cam_mu0), len(lmk_mu0), len(cam_id), L.ptr(cam_id), L.ptr(lmk_id),

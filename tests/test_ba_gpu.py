@@ -176,6 +176,23 @@ def test_tiling_and_landmark_blocking_do_not_change_results(tile, block):
     ref.close(); alt.close()
 
 
+def test_kernel_variants_agree():
+    """The TMA bulk-copy sweep kernel and the first-version LDG kernel are the same arithmetic."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200 import _lib as L
+    G = load_golden("fr1desk_vsmall_huber")
+    gs = [create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=t, kernel_variant=v) for t, v in ((64, 0), (64, 1), (128, 0))]
+    for g in gs:
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+        g.iterate(8); g._eng.fill_iters(8); g.iterate(12, robustify=True)
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ADAPTIVE_VAR, L.F_ITERS, L.F_FLAGS):
+        assert np.array_equal(gs[0]._eng.read(f), gs[1]._eng.read(f)), f
+        assert relerr(gs[2]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, f
+    for g in gs:
+        g.close()
+
+
 def test_synthetic_small_against_oracle():
     """Down-scaled instance of the synthetic generator (configs 4-5): GPU vs oracle, 30 sweeps."""
     from gbp_b200.ba import create_ba_graph
