@@ -140,6 +140,8 @@ def bench_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on STDOUT; keep stdout = one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a dedicated non-default stream shared by torch (events, NCCL ordering, L2 flush) and the engine:
     # the default stream's handle is 0, which the C ABI reads as "create your own stream"
@@ -239,7 +241,6 @@ def bench_ours(args):
     e2e_t = max_over_ranks(float(np.sum(e2e_s)))
     e2e_val = world * args.steps * msgs_per_step / e2e_t
     e2e_parity = float(np.max(np.abs(means - mu_ref)) / np.max(np.abs(mu_ref)))
-    clocks = sampler.stop() if rank == 0 else None
     graph.close()
 
     # ------------------------------------------------------------------ synthetic 10M-factor graph
@@ -247,6 +248,7 @@ def bench_ours(args):
     roofline = roof_fr1
     if not args.no_synthetic:
         synth, roofline = bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, barrier, max_over_ranks)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1)
     cpu = None
