@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -122,10 +123,15 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
             sweep_kernel_ldg<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
         else
             sweep_kernel_ldg<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    } else if (g->cfg.kernel_variant == 2) {   // TMA kernel without L2 eviction hints, for A/B measurements
+        if (g->robust)
+            sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+        else
+            sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
     } else if (g->robust) {
-        sweep_kernel<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
+        sweep_kernel<T, true, true><<<g->n_tiles, T, smem, g->stream>>>(p);
     } else {
-        sweep_kernel<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+        sweep_kernel<T, false, true><<<g->n_tiles, T, smem, g->stream>>>(p);
     }
     g->launches++;
     CU(cudaGetLastError());
@@ -148,10 +154,18 @@ int launch_belief(gbp_ba_graph* g, int finalise) {
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p;
-    p.L = g->L; p.C = g->C; p.lmk_blocks = (g->L + 127) / 128; p.finalise = finalise;
-    const int blocks = p.lmk_blocks + (g->C + 3) / 4;
+    p.L = g->L; p.C = g->C; p.finalise = finalise;
+    static const int lanes_override = getenv("GBP_LMK_LANES") ? atoi(getenv("GBP_LMK_LANES")) : 0;   // experiments only
+    const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : 8);
+    const int per_cta = 128 / lanes;
+    const int blocks = (g->L + per_cta - 1) / per_cta + (g->C + 3) / 4;
     if (blocks == 0) return GBP_OK;
-    belief_kernel<<<blocks, 128, 0, g->stream>>>(p);
+    switch (lanes) {
+        case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
+        case 2: belief_kernel<2><<<blocks, 128, 0, g->stream>>>(p); break;
+        case 4: belief_kernel<4><<<blocks, 128, 0, g->stream>>>(p); break;
+        default: belief_kernel<8><<<blocks, 128, 0, g->stream>>>(p); break;
+    }
     g->launches++;
     CU(cudaGetLastError());
     return GBP_OK;
@@ -314,7 +328,7 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
 
     // ---------------- host graph compiler ----------------
     int T = cfg->tile_edges;
-    if (T == 0) T = F >= 128LL * 148 * 4 ? 128 : (F >= 64LL * 148 * 2 ? 64 : 32);
+    if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
     if (T != 32 && T != 64 && T != 128) { delete g; return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
     g->T = T;
     long long lblock = cfg->lmk_block;

@@ -90,6 +90,35 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// L2 eviction policies: the message / linearisation-point rows are touched once per iteration
+// (evict_first), the landmark belief rows are re-read by other tiles of the same landmark block
+// (evict_last), so 7 GB of streaming rows do not push the 24 MB of hot belief rows out of L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ double2 ldg_hint(const double2* ptr, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -101,6 +130,7 @@ struct EdgeRegs {
     double bl[LMK_B];   // landmark belief row (gathered)
 };
 
+template <bool HINTS>
 __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e, EdgeRegs& r) {
     const int lmk = p.lmk_idx[e];
     r.it = p.iters[e];
@@ -109,9 +139,11 @@ __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e
     r.z[0] = zz.x;
     r.z[1] = zz.y;
     const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
+    uint64_t pol = 0;
+    if (HINTS) pol = policy_evict_last();
 #pragma unroll
     for (int k = 0; k < LMK_B / 2; ++k) {
-        const double2 v = __ldg(src + k);
+        const double2 v = HINTS ? ldg_hint(src + k, pol) : __ldg(src + k);
         r.bl[2 * k] = v.x;
         r.bl[2 * k + 1] = v.y;
     }
@@ -259,7 +291,7 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
 //                     leave by bulk stores.
 // sweep_kernel_ldg  : first version (cooperative LDG/STS copies), kept for A/B measurements.
 // ----------------------------------------------------------------------------------------
-template <int T, bool ROBUST>
+template <int T, bool ROBUST, bool HINTS>
 __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
     double* s_mc = smem;                 // [T][27]
@@ -280,13 +312,20 @@ __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)n_even * (CAM_M + LMK_M + 9) * 8);
-        bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
-        bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
-        bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
+        if (HINTS) {
+            const uint64_t pol = policy_evict_first();
+            bulk_g2s_hint(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar, pol);
+            bulk_g2s_hint(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar, pol);
+            bulk_g2s_hint(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar, pol);
+        } else {
+            bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
+            bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
+            bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
+        }
     }
     for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
     EdgeRegs r;
-    if (tid < n) load_edge_regs(p, base + tid, r);
+    if (tid < n) load_edge_regs<HINTS>(p, base + tid, r);
     __syncthreads();          // s_cb visible
     mbar_wait(bar, 0);        // bulk loads landed
 
@@ -296,11 +335,22 @@ __global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
     if (tid == 0) {
-        if (p.stages & ST_MESSAGES) {
-            bulk_s2g(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8);
-            bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+        if (HINTS) {
+            // the message rows of the landmark are gathered again by belief_kernel: only the big keyframe rows
+            // and the linearisation points are marked evict_first
+            const uint64_t pol = policy_evict_first();
+            if (p.stages & ST_MESSAGES) {
+                bulk_s2g_hint(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8, pol);
+                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+            }
+            if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
+        } else {
+            if (p.stages & ST_MESSAGES) {
+                bulk_s2g(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8);
+                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+            }
+            if (any_relin) bulk_s2g(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72);
         }
-        if (any_relin) bulk_s2g(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72);
         bulk_commit();
     }
     if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
@@ -331,7 +381,7 @@ __global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
     bool relin = false;
     if (tid < n) {
         EdgeRegs r;
-        load_edge_regs(p, base + tid, r);
+        load_edge_regs<false>(p, base + tid, r);
         relin = edge_sweep<ROBUST>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
     }
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
@@ -369,7 +419,7 @@ struct BeliefParams {
     const double* cam_prior;
     double* cam_belief;
     double* cam_partial;     // [C][27]
-    int L, C, lmk_blocks, finalise;
+    int L, C, finalise;
 };
 
 __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row) {
@@ -386,19 +436,75 @@ __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/,
     }
 }
 
+// 72 B message row (8 B aligned) with 16 B loads: rows of even slots start 16 B aligned, odd ones 8 B later
+__device__ __forceinline__ void load_row9(const double* __restrict__ row, bool even, double v[9]) {
+    if (even) {
+        const double2* r2 = reinterpret_cast<const double2*>(row);
+        const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2), d = __ldg(r2 + 3);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+        v[8] = __ldg(row + 8);
+    } else {
+        v[0] = __ldg(row);
+        const double2* r2 = reinterpret_cast<const double2*>(row + 1);
+        const double2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2), d = __ldg(r2 + 3);
+        v[1] = a.x; v[2] = a.y; v[3] = b.x; v[4] = b.y; v[5] = c.x; v[6] = c.y; v[7] = d.x; v[8] = d.y;
+    }
+}
+
+// LMK_LANES lanes cooperate on one landmark: 8 for small graphs (latency: a landmark of degree 46 is
+// gathered in 6 rounds instead of 46), 1-2 for large ones (throughput: full lanes in the 3x3 solve).
+template <int LMK_LANES>
 __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
-    if ((int)blockIdx.x < p.lmk_blocks) {
-        const int l = blockIdx.x * 128 + threadIdx.x;
-        if (l >= p.L) return;
-        double acc[LMK_M];
+    constexpr int LMK_PER_CTA = 128 / LMK_LANES;
+    const int cam_blocks = (p.C + 3) / 4;
+    if ((int)blockIdx.x < cam_blocks) {
+        // ---- keyframes first in the grid: their serial tile loops overlap the landmark CTAs
+        const int c = (int)blockIdx.x * 4 + (threadIdx.x >> 5);
+        const int lane = threadIdx.x & 31;
+        if (c >= p.C) return;
+        double acc = 0.0;
+        if (lane < CAM_M) {
+            const int t0 = p.cam_tile_ptr[c], t1 = p.cam_tile_ptr[c + 1];
+            int q = t0;
+            for (; q + 8 <= t1; q += 8) {          // 8 independent loads in flight, added in tile order
+                double v[8];
 #pragma unroll
-        for (int k = 0; k < LMK_M; ++k) acc[k] = p.lmk_prior[(long long)l * LMK_M + k];
-        const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
-        for (int q = p0; q < p1; ++q) {
-            const double* row = p.msg_lmk + (long long)p.lmk_slots[q] * LMK_M;
+                for (int k = 0; k < 8; ++k) v[k] = p.tile_partial[(long long)p.cam_tiles[q + k] * CAM_M + lane];
 #pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += __ldg(row + k);
+                for (int k = 0; k < 8; ++k) acc += v[k];
+            }
+            for (; q < t1; ++q) acc += p.tile_partial[(long long)p.cam_tiles[q] * CAM_M + lane];
+            p.cam_partial[(long long)c * CAM_M + lane] = acc;
+            acc += p.cam_prior[(long long)c * CAM_M + lane];
         }
+        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B);
+        return;
+    }
+    // ---- landmarks: LMK_LANES lanes gather one landmark's message rows in parallel, then a
+    //      fixed-shape shuffle tree (deterministic) combines them
+    const int sub = threadIdx.x & (LMK_LANES - 1);
+    const int l = ((int)blockIdx.x - cam_blocks) * LMK_PER_CTA + (threadIdx.x / LMK_LANES);
+    const bool valid = l < p.L;
+    double acc[LMK_M];
+#pragma unroll
+    for (int k = 0; k < LMK_M; ++k) acc[k] = 0.0;
+    if (valid) {
+        const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
+        for (int q = p0 + sub; q < p1; q += LMK_LANES) {
+            const int slot = p.lmk_slots[q];
+            double v[9];
+            load_row9(p.msg_lmk + (long long)slot * LMK_M, (slot & 1) == 0, v);
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += v[k];
+        }
+    }
+#pragma unroll
+    for (int o = LMK_LANES / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < LMK_M; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (valid && sub == 0) {
+#pragma unroll
+        for (int k = 0; k < LMK_M; ++k) acc[k] += p.lmk_prior[(long long)l * LMK_M + k];
         double mu[3];
         spd_solve<3>(acc + 3, acc, mu);
         double2* dst = reinterpret_cast<double2*>(p.lmk_belief + (long long)l * LMK_B);
@@ -408,19 +514,6 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
         dst[3] = make_double2(acc[6], acc[7]);
         dst[4] = make_double2(acc[8], mu[0]);
         dst[5] = make_double2(mu[1], mu[2]);
-    } else {
-        const int warp = ((int)blockIdx.x - p.lmk_blocks) * 4 + (threadIdx.x >> 5);
-        const int lane = threadIdx.x & 31;
-        if (warp >= p.C) return;
-        const int c = warp;
-        double acc = 0.0;
-        if (lane < CAM_M) {
-            const int t0 = p.cam_tile_ptr[c], t1 = p.cam_tile_ptr[c + 1];
-            for (int q = t0; q < t1; ++q) acc += p.tile_partial[(long long)p.cam_tiles[q] * CAM_M + lane];
-            p.cam_partial[(long long)c * CAM_M + lane] = acc;
-            acc += p.cam_prior[(long long)c * CAM_M + lane];
-        }
-        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B);
     }
 }
 
