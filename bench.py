@@ -230,11 +230,15 @@ def bench_ours(args):
         t0 = time.perf_counter()
         p2 = balio.BALProblem(pinned["cam_id"], pinned["lmk_id"], pinned["z"], pinned["cam"], pinned["lmk"], prob.K4)
         g2 = create_ba_graph(p2, CFG, device=local, stream=stream)
+        t1 = time.perf_counter()
         g2.generate_priors_var(weaker_factor=CFG["prior_std_weaker_factor"])
         g2.update_all_beliefs()
+        t2 = time.perf_counter()
         means = client_loop(g2)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if os.environ.get("GBP_BENCH_DEBUG"):
+            print(f"[e2e {it}] create {1e3 * (t1 - t0):.2f} ms  priors {1e3 * (t2 - t1):.2f}  loop {1e3 * (t0 + dt - t2):.2f}  total {1e3 * dt:.2f}", file=sys.stderr)
         g2.close()
         if it >= args.warmup:
             e2e_s.append(dt)

@@ -53,7 +53,7 @@ EXPORTS = [
     "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes",
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
     "gbp_ba_sweep_local", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
-    "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
+    "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
     "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval",
 ]
 
@@ -88,6 +88,14 @@ def load():
     lib.gbp_ba_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.gbp_ba_update_beliefs.argtypes = [vp]
     lib.gbp_ba_metrics.argtypes = [vp, dp]
+    lib.gbp_ba_snapshot_layout.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.gbp_ba_snapshot_async.argtypes = [vp, vp]
+    lib.gbp_ba_snapshot_wait.argtypes = [vp]
+    lib.gbp_ba_iterate_snapshot.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.gbp_host_alloc.argtypes = [C.c_size_t]
+    lib.gbp_host_alloc.restype = vp
+    lib.gbp_host_free.argtypes = [vp]
+    lib.gbp_host_free.restype = None
     lib.gbp_ba_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
     lib.gbp_ba_write.argtypes = [vp, C.c_int, vp, C.c_size_t]
     lib.gbp_ba_fill_iters.argtypes = [vp, C.c_int32]
@@ -112,3 +120,66 @@ def check(status):
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# Page-locked blocks are recycled: cudaHostAlloc / cudaFreeHost cost milliseconds and synchronise the device.
+_PINNED_POOL = {}          # nbytes -> [ptr, ...]
+_PINNED_POOL_CAP = 256 << 20
+_pinned_pool_bytes = 0
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; returns it to the pool when the last array using it dies."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.buf = (C.c_char * nbytes).from_address(ptr)
+
+    def __del__(self):
+        global _pinned_pool_bytes
+        try:
+            if not self.ptr or _lib is None:
+                return
+            if _pinned_pool_bytes + self.nbytes <= _PINNED_POOL_CAP:
+                _PINNED_POOL.setdefault(self.nbytes, []).append(self.ptr)
+                _pinned_pool_bytes += self.nbytes
+            else:
+                _lib.gbp_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (fast asynchronous device->host copies); ordinary memory
+    when page-locked memory is unavailable."""
+    global _pinned_pool_bytes
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    if n == 0:
+        return np.empty(shape, dtype=dtype)
+    n_alloc = (n + 4095) & ~4095
+    free = _PINNED_POOL.get(n_alloc)
+    if free:
+        p = free.pop()
+        _pinned_pool_bytes -= n_alloc
+    else:
+        p = load().gbp_host_alloc(n_alloc)
+    if not p:
+        return np.empty(shape, dtype=dtype)
+    blk = _PinnedBlock(p, n_alloc)
+    arr = np.frombuffer(blk.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return _attach(arr, blk)
+
+
+class _OwnedArray(np.ndarray):
+    """ndarray subclass that only adds a slot to keep the pinned block alive."""
+    _gbp_block = None
+
+    def __array_finalize__(self, obj):
+        self._gbp_block = getattr(obj, "_gbp_block", None)
+
+
+def _attach(arr, blk):
+    out = arr.view(_OwnedArray)
+    out._gbp_block = blk
+    return out

@@ -322,7 +322,14 @@ class BAFactorGraph:
         self._adj_cache = None
         self._csr = {}
         self._res_cache = None
+        self._metric_cache = None
         self._params_dirty = False
+        # small graphs: metrics + belief tables are copied to pinned host buffers right behind every sweep
+        self._eager = (e.C * 33 + e.L * 12) * 8 <= self._EAGER_MAX_BYTES and e.F > 0
+        self._snap_pending = False      # an asynchronous snapshot is in flight / unread
+        self._snap_metrics_ok = False   # ... and its metrics still describe the device state
+        self._snap_region = None        # pinned host image of [metrics | keyframe beliefs | landmark beliefs]
+        self._snap_metrics = None
 
     # ------------------------------------------------------------------ FactorGraph parameters
     def _param(name):  # noqa: N805
@@ -341,7 +348,42 @@ class BAFactorGraph:
     del _param
 
     # ------------------------------------------------------------------ mirrors
+    def _resolve_pending(self):
+        """Wait for the snapshot enqueued behind the last sweep; its belief tables become the valid mirrors."""
+        if not self._snap_pending:
+            return
+        self._eng.snapshot_wait()
+        self._snap_pending = False
+        for f in _BELIEF_FIELDS:
+            m = self._mirrors[f]
+            m.valid, m.dirty = True, False
+        if self._snap_metrics_ok:
+            a, en, n = (float(v) for v in self._snap_metrics)
+            self._metric_cache = (a / self._eng.F, en, int(round(n)))
+
+    def _snapshot_region(self):
+        """Pinned host image of the device's snapshot region; the belief mirrors are views into it."""
+        if self._snap_region is None:
+            e = self._eng
+            total, o_met, o_cam, o_lmk = e.snapshot_layout()
+            reg = L.pinned_empty((total,), np.uint8)
+            self._snap_region = reg
+            self._snap_metrics = reg[o_met:o_met + 24].view(np.float64)
+            for f, off, rows, w in ((L.F_CAM_BELIEF, o_cam, e.C, 33), (L.F_LMK_BELIEF, o_lmk, e.L, 12)):
+                m = self._mirrors.setdefault(f, _Mirror(f))
+                view = reg[off:off + rows * w * 8].view(np.float64).reshape(rows, w)
+                if m.data is not None and m.valid:
+                    view[:] = m.data
+                m.data = view
+        return self._snap_region
+
+    def _enqueue_snapshot(self):
+        self._eng.snapshot_async(self._snapshot_region())
+        self._snap_pending, self._snap_metrics_ok = True, True
+
     def _mirror(self, field):
+        if self._snap_pending and field in _BELIEF_FIELDS:
+            self._resolve_pending()
         m = self._mirrors.get(field)
         if m is None:
             m = self._mirrors[field] = _Mirror(field)
@@ -353,6 +395,8 @@ class BAFactorGraph:
     def _touch(self, field):
         self._mirrors[field].dirty = True
         self._res_cache = None
+        self._metric_cache = None
+        self._snap_metrics_ok = False
         if field == L.F_LINPOINT:
             jm = self._mirrors.get(L.F_JACOBIAN_B)
             if jm is not None:
@@ -372,11 +416,17 @@ class BAFactorGraph:
                 m.dirty = False
 
     def _invalidate(self, fields):
+        self._snap_metrics_ok = False
+        if self._snap_pending and any(f in _BELIEF_FIELDS for f in fields):
+            # the in-flight copy targets the mirrors' buffers: let it land before they are reused
+            self._eng.snapshot_wait()
+            self._snap_pending = False
         for f in fields:
             m = self._mirrors.get(f)
             if m is not None:
                 m.valid = False
         self._res_cache = None
+        self._metric_cache = None
 
     def _adj(self):
         if self._adj_cache is None:
@@ -434,21 +484,39 @@ class BAFactorGraph:
         """gbp/gbp_ba.py:54-59"""
         return list(self._residuals().ravel())
 
+    # Small graphs: the first look at the state after a sweep (are / energy / a mean) fetches the metrics
+    # AND both belief tables with one stream synchronisation; larger graphs fetch lazily per field.
+    _EAGER_MAX_BYTES = 1 << 20
+
+    def _snapshot(self):
+        if self._snap_pending and self._snap_metrics_ok:
+            self._resolve_pending()
+        if self._metric_cache is not None:
+            return self._metric_cache
+        self._resolve_pending()
+        self._flush()
+        e = self._eng
+        if self._eager:
+            # fetch metrics and both belief tables with one copy and one synchronisation
+            self._eng.snapshot_async(self._snapshot_region())
+            self._snap_pending, self._snap_metrics_ok = True, True
+            self._resolve_pending()
+            return self._metric_cache
+        a, en, n = e.metrics()
+        self._metric_cache = (a / e.F if e.F else 0.0, en, n)
+        return self._metric_cache
+
     def are(self):
         """gbp/gbp_ba.py:61-69"""
-        self._flush()
-        return self._eng.metrics()[0] / self._eng.F
+        return self._snapshot()[0]
 
     def energy(self):
         """gbp/gbp.py:36-44"""
-        self._flush()
-        return self._eng.metrics()[1]
+        return self._snapshot()[1]
 
     def metrics(self):
         """ARE, energy and the count of `iters_since_relin == 0` (ba.py:95-100) in ONE device pass."""
-        self._flush()
-        a, en, n = self._eng.metrics()
-        return a / self._eng.F, en, n
+        return self._snapshot()
 
     def n_relinearising(self):
         return self.metrics()[2]
@@ -466,6 +534,12 @@ class BAFactorGraph:
     def synchronous_iteration(self, local_relin=True, robustify=False):
         """gbp/gbp.py:86-92"""
         self._flush()
+        if self._eager:
+            # sweep + beliefs + metrics + copies to the pinned mirrors: one CUDA-graph launch
+            self._invalidate(_BELIEF_FIELDS + _FACTOR_FIELDS_INVALIDATED_BY_SWEEP)
+            self._eng.iterate_snapshot(robustify, local_relin, self._snapshot_region())
+            self._snap_pending, self._snap_metrics_ok = True, True
+            return
         self._eng.iterate(1, robustify=robustify, local_relin=local_relin)
         self._invalidate(_BELIEF_FIELDS + _FACTOR_FIELDS_INVALIDATED_BY_SWEEP)
 
@@ -474,6 +548,8 @@ class BAFactorGraph:
         self._flush()
         self._eng.iterate(n_iters, robustify=robustify, local_relin=local_relin)
         self._invalidate(_BELIEF_FIELDS + _FACTOR_FIELDS_INVALIDATED_BY_SWEEP)
+        if self._eager:
+            self._enqueue_snapshot()
 
     def robustify_all_factors(self):
         """gbp/gbp.py:82-84"""
@@ -539,13 +615,18 @@ class BAFactorGraph:
 
     def reset(self):
         """Engine extension: back to the state right after create_ba_graph."""
+        self._resolve_pending()
         self._flush()
         self._eng.reset()
         for m in self._mirrors.values():
             m.valid = False
         self._res_cache = None
+        self._metric_cache = None
 
     def close(self):
+        if self._snap_pending:
+            self._eng.snapshot_wait()
+            self._snap_pending = False
         self._eng.close()
 
 

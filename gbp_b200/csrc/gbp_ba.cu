@@ -42,16 +42,35 @@ int fail(int code, const char* fmt, ...) {
     if (!(h)) return fail(GBP_ERR_INVALID, "null gbp_handle"); \
     CU(cudaSetDevice((h)->device))
 
+// One cudaMalloc per graph: every device array is carved out of a single arena (cudaMalloc / cudaFree
+// cost ~0.5 ms each and cudaFree synchronises the device; a graph has ~30 arrays).
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    static size_t round_up(size_t b) { return (b + 255) & ~size_t(255); }
+    void* take(size_t bytes) {
+        void* p = base ? base + used : nullptr;
+        used += round_up(bytes ? bytes : 1);
+        return p;
+    }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t alloc(size_t count) {
+    bool owned = false;
+    cudaError_t alloc(size_t count) {   // stand-alone allocation (temporaries)
         n = count;
+        owned = true;
         return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
     }
+    void carve(Arena& a, size_t count) {   // with a.base == nullptr this only measures
+        n = count;
+        p = reinterpret_cast<T*>(a.take(count * sizeof(T)));
+    }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
     }
     size_t bytes() const { return n * sizeof(T); }
@@ -85,15 +104,24 @@ struct gbp_ba_graph {
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
+    Arena arena;
+    cudaEvent_t snap_event = nullptr;
+    // fused [iteration + metrics + copies to pinned host buffers] graphs, keyed by stages; valid for snap_ptrs
+    std::map<int, cudaGraphExec_t> snap_graphs;
+    void* snap_ptr = nullptr;
+    size_t snap_bytes = 0;   // metric_out .. end of lmk_belief (start of the arena)
 
     ~gbp_ba_graph() {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        for (auto& kv : snap_graphs) cudaGraphExecDestroy(kv.second);
         tiles.release(); lmk_idx.release(); iters.release(); flags.release(); slot_of_factor.release();
         lmk_ptr.release(); lmk_slots.release(); cam_tile_ptr.release(); cam_tiles.release();
         z.release(); linpoint.release(); msg_cam.release(); msg_lmk.release(); sigma2a.release();
         cam_belief.release(); lmk_belief.release(); cam_prior.release(); lmk_prior.release(); cam_partial.release();
         tile_partial.release(); tile_metric.release(); metric_out.release(); edge_max.release();
         tile_max.release(); cam_max.release(); cam_mu0.release(); lmk_mu0.release();
+        if (arena.base) cudaFree(arena.base);
+        if (snap_event) cudaEventDestroy(snap_event);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -417,18 +445,28 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     };
     cudaError_t e;
-#define ALLOC(buf, n) if ((e = g->buf.alloc(n)) != cudaSuccess) return bail(e, "cudaMalloc " #buf)
     const size_t S = (size_t)g->n_slots;
-    ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
-    ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
-    ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
-    ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * CAM_M); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
-    ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
-    ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
-    ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3); ALLOC(metric_out, 4);
-    ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
-    ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0 measures, pass 1 carves
+        Arena& A = g->arena;
+        A.used = 0;
+#define ALLOC(buf, n) g->buf.carve(A, n)
+        // snapshot region: metrics | keyframe beliefs | landmark beliefs, contiguous -> ONE device->host copy
+        ALLOC(metric_out, 4); ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
+        g->snap_bytes = A.used;
+        ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
+        ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
+        ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
+        ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * CAM_M); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
+        ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
+        ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3);
+        ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+        ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
 #undef ALLOC
+        if (pass == 0) {
+            A.size = A.used;
+            if ((e = cudaMalloc(reinterpret_cast<void**>(&A.base), A.size)) != cudaSuccess) return bail(e, "cudaMalloc arena");
+        }
+    }
 #define UP(buf, vec) if (!(vec).empty() && (e = cudaMemcpyAsync(g->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload " #buf)
     UP(tiles, tiles); UP(lmk_idx, h_lmk_idx); UP(z, h_z); UP(slot_of_factor, g->h_slot_of_factor);
     UP(lmk_ptr, h_lmk_ptr); UP(lmk_slots, h_lmk_slots); UP(cam_tile_ptr, h_cam_tile_ptr); UP(cam_tiles, h_cam_tiles);
@@ -595,6 +633,103 @@ int gbp_ba_metrics(gbp_handle h, double out[3]) {
     return GBP_OK;
 }
 
+namespace {
+int enqueue_metrics(gbp_ba_graph* h) {
+    if (h->n_tiles > 0) {
+        int rc = DISPATCH_T(h, launch_metric_t);
+        if (rc != GBP_OK) return rc;
+        reduce_rows_kernel<3><<<1, 256, 0, h->stream>>>(h->tile_metric.p, h->n_tiles, h->metric_out.p);
+        h->launches += 2;
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemsetAsync(h->metric_out.p, 0, 3 * sizeof(double), h->stream));
+    }
+    return GBP_OK;
+}
+}  // namespace
+
+int gbp_ba_snapshot_layout(gbp_handle h, uint64_t out[4]) {
+    if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
+    out[0] = h->snap_bytes;
+    out[1] = (uint64_t)((char*)h->metric_out.p - h->arena.base);
+    out[2] = (uint64_t)((char*)h->cam_belief.p - h->arena.base);
+    out[3] = (uint64_t)((char*)h->lmk_belief.p - h->arena.base);
+    return GBP_OK;
+}
+
+int gbp_ba_snapshot_async(gbp_handle h, void* region) {
+    CHECK_H(h);
+    if (!region) return fail(GBP_ERR_INVALID, "null region");
+    if (!h->snap_event) CU(cudaEventCreateWithFlags(&h->snap_event, cudaEventDisableTiming));
+    int rc = enqueue_metrics(h);
+    if (rc != GBP_OK) return rc;
+    CU(cudaMemcpyAsync(region, h->arena.base, h->snap_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->snap_event, h->stream));
+    return GBP_OK;
+}
+
+int gbp_ba_iterate_snapshot(gbp_handle h, int robustify, int local_relin, void* region) {
+    CHECK_H(h);
+    if (!region) return fail(GBP_ERR_INVALID, "null region");
+    if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
+    if (!h->snap_event) CU(cudaEventCreateWithFlags(&h->snap_event, cudaEventDisableTiming));
+    const int st = iteration_stages(robustify, local_relin);
+    if (h->snap_ptr != region) {
+        for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
+        h->snap_graphs.clear();
+        h->snap_ptr = region;
+    }
+    auto it = h->snap_graphs.find(st);
+    cudaGraphExec_t exec = nullptr;
+    if (it != h->snap_graphs.end()) {
+        exec = it->second;
+    } else {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = h->launches;
+        int rc = launch_sweep(h, st);
+        if (rc == GBP_OK) rc = launch_belief(h, 1);
+        if (rc == GBP_OK) rc = enqueue_metrics(h);
+        cudaError_t e = cudaSuccess;
+        if (rc == GBP_OK) e = cudaMemcpyAsync(region, h->arena.base, h->snap_bytes, cudaMemcpyDeviceToHost, h->stream);
+        h->launches = before;
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != GBP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || e2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return fail(GBP_ERR_CUDA, "capture of the iteration+snapshot graph failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        h->snap_graphs[st] = exec;
+    }
+    CU(cudaGraphLaunch(exec, h->stream));
+    h->launches += (h->n_tiles > 0 ? 4 : 1);
+    CU(cudaEventRecord(h->snap_event, h->stream));
+    return GBP_OK;
+}
+
+int gbp_ba_snapshot_wait(gbp_handle h) {
+    CHECK_H(h);
+    if (h->snap_event) CU(cudaEventSynchronize(h->snap_event));
+    return GBP_OK;
+}
+
+void* gbp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (gbp_device_count() <= 0) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void gbp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes) {
     CHECK_H(h);
     FieldInfo fi;
@@ -687,6 +822,8 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
     h->cfg.num_undamped_iters = num_undamped_iters; h->cfg.min_linear_iters = min_linear_iters;
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);  // parameters are baked into captured launches
     h->graphs.clear();
+    for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
+    h->snap_graphs.clear();
     return GBP_OK;
 }
 

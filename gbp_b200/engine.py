@@ -116,6 +116,20 @@ class BAEngine:
         L.check(self._lib.gbp_ba_metrics(self._h, out))
         return float(out[0]), float(out[1]), int(round(out[2]))
 
+    def snapshot_layout(self):
+        out = (C.c_uint64 * 4)()
+        L.check(self._lib.gbp_ba_snapshot_layout(self._h, out))
+        return [int(v) for v in out]
+
+    def snapshot_async(self, region):
+        L.check(self._lib.gbp_ba_snapshot_async(self._h, L.ptr(region)))
+
+    def iterate_snapshot(self, robustify, local_relin, region):
+        L.check(self._lib.gbp_ba_iterate_snapshot(self._h, int(bool(robustify)), int(bool(local_relin)), L.ptr(region)))
+
+    def snapshot_wait(self):
+        L.check(self._lib.gbp_ba_snapshot_wait(self._h))
+
     def fill_iters(self, value):
         L.check(self._lib.gbp_ba_fill_iters(self._h, int(value)))
 
@@ -148,7 +162,7 @@ class BAEngine:
         kind, dt, w = L.FIELD_SHAPES[field]
         n = self._rows(kind)
         if out is None:
-            out = np.empty((n, w), dtype=dt)
+            out = L.pinned_empty((n, w), dt)
         assert out.dtype == dt and out.size == n * w and out.flags.c_contiguous
         L.check(self._lib.gbp_ba_read(self._h, int(field), L.ptr(out), out.nbytes))
         return out

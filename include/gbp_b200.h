@@ -144,6 +144,24 @@ int gbp_ba_update_beliefs(gbp_handle h);
  * (NOT yet divided by F), out[1] = energy, out[2] = count.  Synchronises the stream. */
 int gbp_ba_metrics(gbp_handle h, double out[3]);
 
+/* Snapshot = what the client of ba.py looks at between two sweeps (ba.py:95-103): the three numbers of
+ * gbp_ba_metrics and both belief tables.  They are contiguous on the device, so a snapshot is ONE
+ * device->host copy into a caller-owned PAGE-LOCKED region (gbp_host_alloc) of out[0] bytes with the
+ * metrics at byte offset out[1], the keyframe rows (GBP_F_CAM_BELIEF layout) at out[2] and the landmark
+ * rows at out[3]. */
+int gbp_ba_snapshot_layout(gbp_handle h, uint64_t out[4]);
+/* Enqueue metrics + copy behind the work already on the stream; no host synchronisation.  The region must
+ * stay alive until gbp_ba_snapshot_wait returns. */
+int gbp_ba_snapshot_async(gbp_handle h, void* region);
+int gbp_ba_snapshot_wait(gbp_handle h);
+/* One synchronous_iteration (gbp/gbp.py:86-92) immediately followed by a snapshot, replayed as ONE CUDA
+ * graph (sweep, beliefs, metrics, copy): the whole loop body of ba.py:95-105 in a single launch. */
+int gbp_ba_iterate_snapshot(gbp_handle h, int robustify, int local_relin, void* region);
+/* Page-locked host memory for the destination buffers of reads (NULL when no device / out of memory:
+ * callers then use ordinary memory). */
+void* gbp_host_alloc(size_t bytes);
+void gbp_host_free(void* p);
+
 /* Field access (synchronises the stream).  `bytes` must equal rows x row bytes of the field. */
 int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes);
 int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes);
