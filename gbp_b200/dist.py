@@ -109,7 +109,8 @@ class PartitionedBAGraph:
     """`synchronous_iteration` / `generate_priors_var` / `are` / `energy` over a landmark-partitioned graph."""
 
     def __init__(self, prob: BALProblem, configs, rank=0, world=1, device=0, stream=None, dist=None,
-                 engine_factory=None, **engine_kw):
+                 engine_factory=None, torch_stream=None, **engine_kw):
+        engine_kw_stream = torch_stream
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs an initialised torch.distributed module")
         self.rank, self.world, self.dist = rank, world, dist
@@ -118,6 +119,8 @@ class PartitionedBAGraph:
         factory = engine_factory or (lambda s, c: CudaEngineAdapter(s, c, device, stream, **engine_kw))
         self.adapter = factory(sub, configs)
         self._gather = self.adapter.new_gather_buffer(world) if world > 1 else None
+        self._graphs = {}        # stages -> captured CUDA graph of [local sweep, all-gather, keyframe update]
+        self._torch_stream = engine_kw_stream
 
     @property
     def engine(self):
@@ -162,8 +165,34 @@ class PartitionedBAGraph:
             st |= L.ST_ROBUSTIFY
         if local_relin:
             st |= L.ST_RELIN | L.ST_LOCAL_DAMPING
+        g = self._graphs.get(st)
+        if g is not None:
+            g.replay()
+            return
         self.adapter.sweep_local(st)
         self._exchange_and_update()
+
+    def capture(self, local_relin=True, robustify=False):
+        """Capture [local sweep -> all-gather -> keyframe update] of one synchronous iteration into a CUDA graph
+        (NCCL collectives are capturable), so that an iteration is ONE launch per rank instead of three engine
+        calls plus a Python-side collective.  Needs the torch stream the engine was created on."""
+        if self.world == 1 or self._torch_stream is None:
+            return False
+        import torch
+        st = L.ST_MESSAGES | L.ST_BELIEFS | (L.ST_ROBUSTIFY if robustify else 0) | \
+            ((L.ST_RELIN | L.ST_LOCAL_DAMPING) if local_relin else 0)
+        if st in self._graphs:
+            return True
+        # one eager iteration first: NCCL sets up its channels outside the capture
+        self.adapter.sweep_local(st)
+        self._exchange_and_update()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._torch_stream, capture_error_mode="thread_local"):
+            self.adapter.sweep_local(st)
+            self._exchange_and_update()
+        self._graphs[st] = g
+        return True
 
     def fill_iters(self, value):
         self.adapter.fill_iters(value)
@@ -195,4 +224,9 @@ class PartitionedBAGraph:
         return np.concatenate([cam, lmk.ravel()])
 
     def close(self):
+        # captured graphs hold NCCL work: they must die before the process group is destroyed
+        if self._graphs:
+            import torch
+            torch.cuda.synchronize()
+            self._graphs.clear()
         self.adapter.close()

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out_dir):
     from gbp_b200.dist import PartitionedBAGraph
     from gbp_b200.synthetic import make_synthetic
     prob = make_synthetic(40, 6000, 8, seed=5)
-    pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=rank, stream=s.cuda_stream, dist=dist)
+    pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=rank, stream=s.cuda_stream, dist=dist, torch_stream=s)
     pg.generate_priors_var(50.0)
     pg.update_all_beliefs()
     trace = []
@@ -34,7 +34,10 @@ def _worker(rank, world, port, out_dir):
         if i in (3, 8):
             pg.fill_iters(1)
         trace.append(pg.metrics())
-        pg.synchronous_iteration(robustify=True, local_relin=True)
+        if i == 12:
+            assert pg.capture(local_relin=True, robustify=True)   # capture() itself runs one eager iteration
+        else:
+            pg.synchronous_iteration(robustify=True, local_relin=True)
     trace.append(pg.metrics())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace))
     pg.close()
