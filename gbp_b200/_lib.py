@@ -54,7 +54,7 @@ EXPORTS = [
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
     "gbp_ba_sweep_local", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
-    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval",
+    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
 ]
 
 _lib = None
@@ -107,6 +107,11 @@ def load():
     lib.gbp_ba_launch_count.argtypes = [vp]
     lib.gbp_ba_launch_count.restype = C.c_int64
     lib.gbp_reprojection_eval.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp]
+    lib.gbp_bal_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.gbp_bal_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.gbp_bal_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.gbp_bal_close.argtypes = [vp]
+    lib.gbp_bal_close.restype = None
     if lib.gbp_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libgbp_b200 ABI {lib.gbp_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib

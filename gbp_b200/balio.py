@@ -48,9 +48,29 @@ class BALProblem:
 
 
 def read_bal(path) -> BALProblem:
+    """BAL text file (native parser in libgbp_b200, `gbp_bal_open`) or the `.npz` container."""
     if str(path).endswith(".npz"):
         d = np.load(path)
         return BALProblem(d["cam_id"], d["lmk_id"], d["z"], d["cam_means"], d["lmk_means"], d["K4"])
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load()
+    h = C.c_void_p()
+    L.check(lib.gbp_bal_open(str(path).encode(), C.byref(h)))
+    try:
+        n = (C.c_int64 * 3)()
+        L.check(lib.gbp_bal_sizes(h, n))
+        nc, nl, nf = (int(v) for v in n)
+        cam_id, lmk_id = np.empty(nf, np.int32), np.empty(nf, np.int32)
+        z, cam, lmk, K4 = np.empty((nf, 2)), np.empty((nc, 6)), np.empty((nl, 3)), np.empty(4)
+        L.check(lib.gbp_bal_copy(h, L.ptr(cam_id), L.ptr(lmk_id), L.ptr(z), L.ptr(cam), L.ptr(lmk), L.ptr(K4)))
+    finally:
+        lib.gbp_bal_close(h)
+    return BALProblem(cam_id, lmk_id, z, cam, lmk, K4)
+
+
+def read_bal_python(path) -> BALProblem:
+    """Pure-Python reader with the same rules (cross-check of the native parser in the tests)."""
     with open(path, "r") as f:
         lines = f.read().split("\n")
     # header: skip blank lines and '# ...' comment lines (utils/read_balfile.py:7-11)

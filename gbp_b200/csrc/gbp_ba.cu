@@ -906,3 +906,5 @@ int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int dev
 }
 
 }  // extern "C"
+
+#include "gbp_bal.cpp.inc"

@@ -188,6 +188,17 @@ int64_t gbp_ba_launch_count(gbp_handle h);
 int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int device, double* out_h,
                           double* out_J);
 
+/* ---- BAL-style problem files (host only; no device needed) -------------------------------------------
+ * Native replacement of read_balfile (utils/read_balfile.py:4-37): same acceptance rules (leading blank /
+ * "# ..." lines skipped; first four tokens of a measurement line; first token of a parameter line).
+ * gbp_bal_open parses the whole file; gbp_bal_copy fills caller-owned arrays (any pointer may be NULL). */
+typedef struct gbp_bal_file gbp_bal_file;
+int gbp_bal_open(const char* path, gbp_bal_file** out);
+int gbp_bal_sizes(const gbp_bal_file* bal, int64_t out[3] /* keyframes, landmarks, measurements */);
+int gbp_bal_copy(const gbp_bal_file* bal, int32_t* cam_id, int32_t* lmk_id, double* z /* F x 2 */,
+                 double* cam_means /* C x 6 */, double* lmk_means /* L x 3 */, double K4[4]);
+void gbp_bal_close(gbp_bal_file* bal);
+
 #ifdef __cplusplus
 }
 #endif

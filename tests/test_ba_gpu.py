@@ -332,3 +332,51 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         g.factors[0].eta_damping = 0.123
     g.close()
+
+
+def test_client_script_trace(tmp_path, capsys):
+    """examples/ba_client.py (the call sequence and printed trace of ba.py:48-105, including the Python loops over
+    graph.factors) on fr1desk_vsmall read from a BAL text file, against the reference's trace."""
+    import importlib.util
+    from gbp_b200 import balio
+    from conftest import ROOT
+    import os
+    G = load_golden("fr1desk_vsmall")
+    path = str(tmp_path / "fr1desk_vsmall.txt")
+    balio.write_bal(path, golden_problem(G), ["fr1desk_vsmall (from the fixture)"])
+    spec = importlib.util.spec_from_file_location("ba_client", os.path.join(ROOT, "examples", "ba_client.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    graph, trace = mod.main(["--bal_file", path, "--n_iters", "20"])
+    trace = np.array(trace)
+    assert relerr(trace[:, 0], G["are"][:20]) < 1e-7 and relerr(trace[:, 1], G["energy"][:20]) < 1e-7
+    assert np.array_equal(trace[:, 2].astype(int), G["n_relin"][:20])
+    out = capsys.readouterr().out
+    assert "Number of keyframes: 10" in out and "Iteration 16 // ARE 23.6383" in out
+    graph.close()
+
+
+def test_snapshot_paths_agree():
+    """Eager (fused graph + pinned snapshot) and lazy reads return the same numbers as explicit reads."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200 import _lib as L
+    G = load_golden("fr1desk_vsmall")
+    g = create_ba_graph(golden_problem(G), golden_configs(G))
+    assert g._eager
+    g.generate_priors_var(50.0); g.update_all_beliefs()
+    for i in range(5):
+        g.synchronous_iteration(robustify=True, local_relin=True)       # fused path, snapshot pending
+        if i % 2:
+            g.synchronous_iteration(robustify=True, local_relin=True)   # two in a row without reading
+        a, e, n = g.metrics()
+        sa, se, sn = g._eng.metrics()
+        assert (a, e, n) == (sa / g._eng.F, se, sn)
+        assert np.array_equal(g.cam_nodes[2].mu, g._eng.read(L.F_CAM_BELIEF)[2, 27:])
+        assert np.array_equal(g.lmk_nodes[5].belief.eta, g._eng.read(L.F_LMK_BELIEF)[5, :3])
+        g.lmk_nodes[5].mu = g.lmk_nodes[5].mu + 1e-3                    # client write while mirrors are hot
+        g.factors[3].iters_since_relin = 4
+    g._flush()                                                          # pending client writes reach the device
+    assert g._eng.read(L.F_ITERS)[3, 0] == g.factors[3].iters_since_relin == 4
+    g.reset()
+    assert g._eng.read(L.F_MSG_CAM).max() == 0.0 and not g._snap_pending
+    g.close()
