@@ -349,7 +349,7 @@ def test_client_script_trace(tmp_path, capsys):
     spec.loader.exec_module(mod)
     graph, trace = mod.main(["--bal_file", path, "--n_iters", "20"])
     trace = np.array(trace)
-    assert relerr(trace[:, 0], G["are"][:20]) < 1e-7 and relerr(trace[:, 1], G["energy"][:20]) < 1e-7
+    assert relerr(trace[:, 0], G["are"][:20]) < 1e-6 and relerr(trace[:, 1], G["energy"][:20]) < 1e-6   # same tolerance as the trajectory tests
     assert np.array_equal(trace[:, 2].astype(int), G["n_relin"][:20])
     out = capsys.readouterr().out
     assert "Number of keyframes: 10" in out and "Iteration 16 // ARE 23.6383" in out
