@@ -151,6 +151,11 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
             sweep_kernel_ldg<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
         else
             sweep_kernel_ldg<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    } else if (g->cfg.kernel_variant == 3) {   // TMA + hints, compiled for 16 warps per SM (128 registers)
+        if (g->robust)
+            sweep_kernel<T, true, true, 1><<<g->n_tiles, T, smem, g->stream>>>(p);
+        else
+            sweep_kernel<T, false, true, 1><<<g->n_tiles, T, smem, g->stream>>>(p);
     } else if (g->cfg.kernel_variant == 2) {   // TMA kernel without L2 eviction hints, for A/B measurements
         if (g->robust)
             sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);

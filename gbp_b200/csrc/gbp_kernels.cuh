@@ -176,7 +176,7 @@ __device__ __forceinline__ bool edge_sweep(const SweepParams& p, long long e, Ed
             const double d = x0[6 + k] - bl[9 + k];
             d2 += d * d;
         }
-        relin = (sqrt(d2) > p.beta) && (it >= p.min_linear);
+        relin = (d2 > p.beta * p.beta) && (it >= p.min_linear);   // |.| > beta without the square root
     }
 
     double var = p.var0;
@@ -291,8 +291,10 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
 //                     leave by bulk stores.
 // sweep_kernel_ldg  : first version (cooperative LDG/STS copies), kept for A/B measurements.
 // ----------------------------------------------------------------------------------------
-template <int T, bool ROBUST, bool HINTS>
-__global__ void __launch_bounds__(T) sweep_kernel(const SweepParams p) {
+// Compiled for 384 resident threads per SM (<= 170 registers, no spills).  OCC = 1: 512 threads per SM (128 registers,
+// a few spilled doubles) -- measured SLOWER (1.32 vs 1.25 ms on the 10 M-factor graph), kept as kernel_variant 3 for A/B.
+template <int T, bool ROBUST, bool HINTS, int OCC = 0>
+__global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
     double* s_mc = smem;                 // [T][27]
     double* s_ml = s_mc + T * CAM_M;     // [T][9]
