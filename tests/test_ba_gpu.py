@@ -380,3 +380,56 @@ def test_snapshot_paths_agree():
     g.reset()
     assert g._eng.read(L.F_MSG_CAM).max() == 0.0 and not g._snap_pending
     g.close()
+
+
+def test_full_size_properties():
+    """Size-independent properties on a large synthetic graph (2 M factors; the 10 M-factor configuration is the
+    same code path and is exercised by bench.py): every belief is exactly prior + the sum of its incoming
+    messages (linearity / checksum of checksums), messages are symmetric rank-2 PSD, means solve Lambda mu = eta,
+    every factor relinearises on schedule, and the result does not depend on the engine's storage order."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.engine import unpack_sym
+    from gbp_b200.synthetic import make_synthetic
+    from gbp_b200 import _lib as L
+    prob = make_synthetic(200, 200_000, 10, seed=1)
+    cfg = dict(gauss_noise_std=2, loss="huber", Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8,
+               eta_damping=0.4)
+    g = create_ba_graph(prob, cfg)
+    assert g._eng.F == 2_000_000 and g._eng.tile_edges == 64
+    g.generate_priors_var(50.0)
+    g.update_all_beliefs()
+    g.iterate(12, robustify=True, local_relin=True)
+    e = g._eng
+    adj = e.read(L.F_ADJ)
+    mc, ml = e.read(L.F_MSG_CAM), e.read(L.F_MSG_LMK)
+    cb, lb = e.read(L.F_CAM_BELIEF), e.read(L.F_LMK_BELIEF)
+    cp, lp = e.read(L.F_CAM_PRIOR), e.read(L.F_LMK_PRIOR)
+    # (1) beliefs = prior + sum of incoming messages, for ALL variables (float64 sums in a different order)
+    cs = cp.copy(); np.add.at(cs, adj[:, 0], mc)
+    ls = lp.copy(); np.add.at(ls, adj[:, 1], ml)
+    assert relerr(cb[:, :27], cs) < 1e-12 and relerr(lb[:, :9], ls) < 1e-12
+    # (2) means solve the belief system
+    lam_c, lam_l = unpack_sym(cb[:, 6:27], 6), unpack_sym(lb[:, 3:9], 3)
+    assert relerr(np.einsum("vij,vj->vi", lam_c, cb[:, 27:]), cb[:, :6]) < 1e-9
+    assert relerr(np.einsum("vij,vj->vi", lam_l, lb[:, 9:]), lb[:, :3]) < 1e-9
+    # (3) messages: symmetric PSD of rank <= 2 (sample)
+    idx = np.linspace(0, e.F - 1, 5000).astype(int)
+    ev = np.linalg.eigvalsh(unpack_sym(mc[idx, 6:], 6))
+    assert ev.min() > -1e-9 * ev.max() and np.all(ev[:, :4].max(axis=1) < 1e-9 * ev[:, 5] + 1e-300)
+    ev3 = np.linalg.eigvalsh(unpack_sym(ml[idx, 3:], 3))
+    assert ev3.min() > -1e-9 * ev3.max() and np.all(ev3[:, 0] < 1e-9 * ev3[:, 2] + 1e-300)
+    # (4) relinearisation schedule without client resets: iters_since_relin starts at 1, reaches min_linear_iters = 8
+    #     before sweep 7, the factor relinearises there (-> 0) and counts 4 more sweeps; factors that never moved read 13
+    its = e.read(L.F_ITERS)[:, 0]
+    #     (a factor whose mean had moved less than beta at sweep 7 relinearises one to three sweeps later)
+    assert set(np.unique(its).tolist()) <= {0, 1, 2, 3, 4, 13} and (its == 4).mean() > 0.9
+    assert np.isfinite(cb).all() and np.isfinite(lb).all() and np.isfinite(mc).all()
+    # (5) storage order (tiles, landmark blocks) and kernel variant do not change the state
+    h = create_ba_graph(prob, cfg, tile_edges=128, lmk_block=50_000, kernel_variant=2)
+    h.generate_priors_var(50.0)
+    h.update_all_beliefs()
+    h.iterate(12, robustify=True, local_relin=True)
+    assert relerr(h._eng.read(L.F_LMK_BELIEF), lb) < 1e-9 and relerr(h._eng.read(L.F_CAM_BELIEF), cb) < 1e-9
+    a1, a2 = g.are(), h.are()
+    assert abs(a1 - a2) < 1e-9 * a1 and a1 < 5.0
+    g.close(); h.close()
