@@ -16,7 +16,7 @@ ABI_VERSION = 1
 
 # gbp_field
 (F_CAM_BELIEF, F_LMK_BELIEF, F_CAM_PRIOR, F_LMK_PRIOR, F_MSG_CAM, F_MSG_LMK, F_LINPOINT, F_ITERS,
- F_FLAGS, F_ADAPTIVE_VAR, F_MEASUREMENT, F_JACOBIAN_B, F_ADJ, F_FILE_INDEX, F_CAM_PARTIAL) = range(15)
+ F_FLAGS, F_ADAPTIVE_VAR, F_MEASUREMENT, F_JACOBIAN_B, F_ADJ, F_FILE_INDEX, F_CAM_PARTIAL, F_CAM_MU, F_LMK_MU) = range(17)
 
 # stages
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING = 1, 2, 4, 8, 16
@@ -31,7 +31,7 @@ FIELD_SHAPES = {
     F_LINPOINT: ("F", np.float64, 9), F_ITERS: ("F", np.int32, 1), F_FLAGS: ("F", np.int32, 1),
     F_ADAPTIVE_VAR: ("F", np.float64, 1), F_MEASUREMENT: ("F", np.float64, 2),
     F_JACOBIAN_B: ("F", np.float64, 20), F_ADJ: ("F", np.int32, 2), F_FILE_INDEX: ("F", np.int32, 1),
-    F_CAM_PARTIAL: ("C", np.float64, 27),
+    F_CAM_PARTIAL: ("C", np.float64, 27), F_CAM_MU: ("C", np.float64, 6), F_LMK_MU: ("L", np.float64, 3),
 }
 
 

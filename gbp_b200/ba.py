@@ -89,7 +89,11 @@ class _VariableNode:
     @property
     def mu(self):
         n = self.dofs
-        return self._g._mirror(self._bfield())[self._i, -n:].copy()
+        g = self._g
+        bm = g._mirrors.get(self._bfield())
+        if bm is not None and bm.valid and not g._snap_pending:
+            return bm.data[self._i, -n:].copy()            # full belief table already on the host (maybe edited)
+        return g._mirror(L.F_CAM_MU if self._is_cam else L.F_LMK_MU)[self._i].copy()
 
     @mu.setter
     def mu(self, value):
@@ -290,7 +294,8 @@ class _ConcatSeq(_LazySeq):
 
 _FACTOR_FIELDS_INVALIDATED_BY_SWEEP = (L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ITERS, L.F_FLAGS,
                                        L.F_ADAPTIVE_VAR, L.F_JACOBIAN_B)
-_BELIEF_FIELDS = (L.F_CAM_BELIEF, L.F_LMK_BELIEF)
+_BELIEF_FIELDS = (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_CAM_MU, L.F_LMK_MU)
+_MU_FIELDS = (L.F_CAM_MU, L.F_LMK_MU)
 
 
 class BAFactorGraph:
@@ -325,7 +330,7 @@ class BAFactorGraph:
         self._metric_cache = None
         self._params_dirty = False
         # small graphs: metrics + belief tables are copied to pinned host buffers right behind every sweep
-        self._eager = (e.C * 33 + e.L * 12) * 8 <= self._EAGER_MAX_BYTES and e.F > 0
+        self._eager = (e.C * 6 + e.L * 3) * 8 <= self._EAGER_MAX_BYTES and e.F > 0
         self._snap_pending = False      # an asynchronous snapshot is in flight / unread
         self._snap_metrics_ok = False   # ... and its metrics still describe the device state
         self._snap_region = None        # pinned host image of [metrics | keyframe beliefs | landmark beliefs]
@@ -354,7 +359,7 @@ class BAFactorGraph:
             return
         self._eng.snapshot_wait()
         self._snap_pending = False
-        for f in _BELIEF_FIELDS:
+        for f in _MU_FIELDS:
             m = self._mirrors[f]
             m.valid, m.dirty = True, False
         if self._snap_metrics_ok:
@@ -362,14 +367,15 @@ class BAFactorGraph:
             self._metric_cache = (a / self._eng.F, en, int(round(n)))
 
     def _snapshot_region(self):
-        """Pinned host image of the device's snapshot region; the belief mirrors are views into it."""
+        """Pinned host image of the device's snapshot region [metrics | keyframe means | landmark means]; the mean
+        mirrors are views into it."""
         if self._snap_region is None:
             e = self._eng
             total, o_met, o_cam, o_lmk = e.snapshot_layout()
             reg = L.pinned_empty((total,), np.uint8)
             self._snap_region = reg
             self._snap_metrics = reg[o_met:o_met + 24].view(np.float64)
-            for f, off, rows, w in ((L.F_CAM_BELIEF, o_cam, e.C, 33), (L.F_LMK_BELIEF, o_lmk, e.L, 12)):
+            for f, off, rows, w in ((L.F_CAM_MU, o_cam, e.C, 6), (L.F_LMK_MU, o_lmk, e.L, 3)):
                 m = self._mirrors.setdefault(f, _Mirror(f))
                 view = reg[off:off + rows * w * 8].view(np.float64).reshape(rows, w)
                 if m.data is not None and m.valid:
@@ -384,6 +390,11 @@ class BAFactorGraph:
     def _mirror(self, field):
         if self._snap_pending and field in _BELIEF_FIELDS:
             self._resolve_pending()
+        if field in _MU_FIELDS:
+            # a belief table edited on the host (client assigned node.mu / belief) supersedes the compact means
+            bm = self._mirrors.get(L.F_CAM_BELIEF if field == L.F_CAM_MU else L.F_LMK_BELIEF)
+            if bm is not None and bm.dirty:
+                self._flush()
         m = self._mirrors.get(field)
         if m is None:
             m = self._mirrors[field] = _Mirror(field)
@@ -414,6 +425,11 @@ class BAFactorGraph:
                 else:
                     self._eng.write(m.field, m.data)
                 m.dirty = False
+                if m.field in (L.F_CAM_BELIEF, L.F_LMK_BELIEF):
+                    # the device refreshed its compact means from the table just written; the host copy is stale
+                    mm = self._mirrors.get(L.F_CAM_MU if m.field == L.F_CAM_BELIEF else L.F_LMK_MU)
+                    if mm is not None:
+                        mm.valid = False
 
     def _invalidate(self, fields):
         self._snap_metrics_ok = False
@@ -449,8 +465,8 @@ class BAFactorGraph:
         if self._res_cache is None:
             from .engine import reprojection_eval
             adj = self._adj()
-            cm = self._mirror(L.F_CAM_BELIEF)[:, 27:]
-            lm = self._mirror(L.F_LMK_BELIEF)[:, 9:]
+            cm = self._mirror(L.F_CAM_MU)
+            lm = self._mirror(L.F_LMK_MU)
             x = np.concatenate([cm[adj[:, 0]], lm[adj[:, 1]]], axis=1)
             h, _ = reprojection_eval(x, self._eng.K4, self._eng.device)
             self._res_cache = h - self._mirror(L.F_MEASUREMENT)
@@ -572,15 +588,15 @@ class BAFactorGraph:
     def compute_all_factors(self):
         """gbp/gbp.py:60-62: relinearise every factor at the current adjacent belief means."""
         adj = self._adj()
-        cm = self._mirror(L.F_CAM_BELIEF)[:, 27:]
-        lm = self._mirror(L.F_LMK_BELIEF)[:, 9:]
+        cm = self._mirror(L.F_CAM_MU)
+        lm = self._mirror(L.F_LMK_MU)
         self._mirror(L.F_LINPOINT)[:] = np.concatenate([cm[adj[:, 0]], lm[adj[:, 1]]], axis=1)
         self._touch(L.F_LINPOINT)
         self._flush()
 
     def get_means(self):
         """gbp/gbp.py:146-153"""
-        return np.concatenate([self._mirror(L.F_CAM_BELIEF)[:, 27:].ravel(), self._mirror(L.F_LMK_BELIEF)[:, 9:].ravel()])
+        return np.concatenate([self._mirror(L.F_CAM_MU).ravel(), self._mirror(L.F_LMK_MU).ravel()])
 
     def joint_distribution_inf(self):
         """gbp/gbp.py:94-134 (dense; small graphs only)."""

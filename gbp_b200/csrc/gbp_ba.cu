@@ -100,7 +100,7 @@ struct gbp_ba_graph {
     DevBuf<Tile> tiles;
     DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
-    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0;
+    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
@@ -186,7 +186,7 @@ int launch_belief(gbp_ba_graph* g, int finalise) {
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
-    p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p;
+    p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.L = g->L; p.C = g->C; p.finalise = finalise;
     static const int lanes_override = getenv("GBP_LMK_LANES") ? atoi(getenv("GBP_LMK_LANES")) : 0;   // experiments only
     const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : 8);
@@ -259,6 +259,8 @@ bool field_info(int field, FieldInfo* fi) {
         case GBP_F_ADJ: *fi = {2, 2, false}; return true;
         case GBP_F_FILE_INDEX: *fi = {2, 1, false}; return true;
         case GBP_F_CAM_PARTIAL: *fi = {0, CAM_M * 2, false}; return true;
+        case GBP_F_CAM_MU: *fi = {0, 12, false}; return true;
+        case GBP_F_LMK_MU: *fi = {1, 6, false}; return true;
         default: return false;
     }
 }
@@ -277,6 +279,8 @@ void* field_dev_ptr(gbp_ba_graph* g, int field) {
         case GBP_F_ADAPTIVE_VAR: return g->sigma2a.p;
         case GBP_F_MEASUREMENT: return g->z.p;
         case GBP_F_CAM_PARTIAL: return g->cam_partial.p;
+        case GBP_F_CAM_MU: return g->cam_mu.p;
+        case GBP_F_LMK_MU: return g->lmk_mu.p;
         default: return nullptr;
     }
 }
@@ -455,9 +459,10 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         Arena& A = g->arena;
         A.used = 0;
 #define ALLOC(buf, n) g->buf.carve(A, n)
-        // snapshot region: metrics | keyframe beliefs | landmark beliefs, contiguous -> ONE device->host copy
-        ALLOC(metric_out, 4); ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
+        // snapshot region: metrics | keyframe means | landmark means, contiguous -> ONE small device->host copy
+        ALLOC(metric_out, 4); ALLOC(cam_mu, (size_t)C * 6); ALLOC(lmk_mu, (size_t)L * 3);
         g->snap_bytes = A.used;
+        ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
         ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
         ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
@@ -494,8 +499,8 @@ int gbp_ba_reset(gbp_handle h) {
     ZERO(edge_max); ZERO(tile_max); ZERO(cam_max);
 #undef ZERO
     // beliefs: eta = Lambda = 0, mu = initial means; edges linearised at those means
-    if (g->C > 0) init_belief_kernel<<<(g->C + 127) / 128, 128, 0, g->stream>>>(g->cam_mu0.p, g->C, 6, CAM_B, g->cam_belief.p);
-    if (g->L > 0) init_belief_kernel<<<(g->L + 127) / 128, 128, 0, g->stream>>>(g->lmk_mu0.p, g->L, 3, LMK_B, g->lmk_belief.p);
+    if (g->C > 0) init_belief_kernel<<<(g->C + 127) / 128, 128, 0, g->stream>>>(g->cam_mu0.p, g->C, 6, CAM_B, g->cam_belief.p, g->cam_mu.p);
+    if (g->L > 0) init_belief_kernel<<<(g->L + 127) / 128, 128, 0, g->stream>>>(g->lmk_mu0.p, g->L, 3, LMK_B, g->lmk_belief.p, g->lmk_mu.p);
     CU(cudaGetLastError());
     if (g->n_tiles > 0) {
         int rc = DISPATCH_T(g, launch_init_t);
@@ -596,7 +601,7 @@ int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {
     const double* src = partials_dev ? partials_dev : h->cam_partial.p;
     if (!partials_dev) nranks = 1;
     if (nranks < 1) return fail(GBP_ERR_INVALID, "nranks must be >= 1");
-    cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p);
+    cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p, h->cam_mu.p);
     h->launches++;
     CU(cudaGetLastError());
     return GBP_OK;
@@ -657,8 +662,8 @@ int gbp_ba_snapshot_layout(gbp_handle h, uint64_t out[4]) {
     if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
     out[0] = h->snap_bytes;
     out[1] = (uint64_t)((char*)h->metric_out.p - h->arena.base);
-    out[2] = (uint64_t)((char*)h->cam_belief.p - h->arena.base);
-    out[3] = (uint64_t)((char*)h->lmk_belief.p - h->arena.base);
+    out[2] = (uint64_t)((char*)h->cam_mu.p - h->arena.base);
+    out[3] = (uint64_t)((char*)h->lmk_mu.p - h->arena.base);
     return GBP_OK;
 }
 
@@ -781,6 +786,9 @@ int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes) {
     if (!host_src) return fail(GBP_ERR_INVALID, "null source");
     if (fi.indexed != 2) {
         CU(cudaMemcpyAsync(field_dev_ptr(h, field), host_src, need, cudaMemcpyHostToDevice, h->stream));
+        if (field == GBP_F_CAM_BELIEF) extract_mu_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_belief.p, h->C, 6, CAM_B, h->cam_mu.p);
+        if (field == GBP_F_LMK_BELIEF) extract_mu_kernel<<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->lmk_belief.p, h->L, 3, LMK_B, h->lmk_mu.p);
+        CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
         if (field == GBP_F_CAM_PRIOR || field == GBP_F_LMK_PRIOR) h->priors_set = true;
         return GBP_OK;

@@ -421,10 +421,12 @@ struct BeliefParams {
     const double* cam_prior;
     double* cam_belief;
     double* cam_partial;     // [C][27]
+    double* cam_mu;          // [C][6]  compact copy of the means (snapshot region)
+    double* lmk_mu;          // [L][3]
     int L, C, finalise;
 };
 
-__device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row) {
+__device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out) {
     // lanes 0..26 hold eta[6] | Lambda[21]; gather to lane 0, solve, write the 33-double row
     double v[CAM_M];
 #pragma unroll
@@ -434,7 +436,10 @@ __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/,
         double mu[6];
         spd_solve<6>(v + 6, v, mu);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) row[27 + k] = mu[k];
+        for (int k = 0; k < 6; ++k) {
+            row[27 + k] = mu[k];
+            mu_out[k] = mu[k];
+        }
     }
 }
 
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
             p.cam_partial[(long long)c * CAM_M + lane] = acc;
             acc += p.cam_prior[(long long)c * CAM_M + lane];
         }
-        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B);
+        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6);
         return;
     }
     // ---- landmarks: LMK_LANES lanes gather one landmark's message rows in parallel, then a
@@ -516,13 +521,15 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
         dst[3] = make_double2(acc[6], acc[7]);
         dst[4] = make_double2(acc[8], mu[0]);
         dst[5] = make_double2(mu[1], mu[2]);
+        double* m = p.lmk_mu + (long long)l * 3;
+        m[0] = mu[0]; m[1] = mu[1]; m[2] = mu[2];
     }
 }
 
 // keyframe beliefs from gathered per-rank partial sums (multi-GPU): prior + sum_r partial[r]
 __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restrict__ partials, int nranks, int C,
                                                          const double* __restrict__ cam_prior,
-                                                         double* __restrict__ cam_belief) {
+                                                         double* __restrict__ cam_belief, double* __restrict__ cam_mu) {
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restric
         for (int r = 0; r < nranks; ++r) acc += partials[((long long)r * C + c) * CAM_M + lane];
         acc += cam_prior[(long long)c * CAM_M + lane];
     }
-    cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B);
+    cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B, cam_mu + (long long)c * 6);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -741,12 +748,22 @@ __global__ void __launch_bounds__(T) init_edges_kernel(const Tile* tiles, const 
 }
 
 // belief rows from initial means: eta = 0, Lambda = 0, mu = mu0 (gbp/gbp.py:165-168, gbp/gbp_ba.py:116,123)
-__global__ void init_belief_kernel(const double* mu0, int V, int N, int brow, double* belief) {
+__global__ void init_belief_kernel(const double* mu0, int V, int N, int brow, double* belief, double* mu_compact) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     double* row = belief + (long long)v * brow;
     for (int k = 0; k < brow - N; ++k) row[k] = 0.0;
-    for (int k = 0; k < N; ++k) row[brow - N + k] = mu0[(long long)v * N + k];
+    for (int k = 0; k < N; ++k) {
+        row[brow - N + k] = mu0[(long long)v * N + k];
+        mu_compact[(long long)v * N + k] = mu0[(long long)v * N + k];
+    }
+}
+
+// compact means <- mean part of the belief rows (after the client wrote a belief table)
+__global__ void extract_mu_kernel(const double* belief, int V, int N, int brow, double* mu_compact) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    for (int k = 0; k < N; ++k) mu_compact[(long long)v * N + k] = belief[(long long)v * brow + brow - N + k];
 }
 
 // dst[f][w] = src[slot_of_factor[f]][w]  (rows of W 4-byte words)

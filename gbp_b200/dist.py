@@ -93,10 +93,10 @@ class CudaEngineAdapter:
         return np.array([a, e, float(n)])
 
     def cam_means(self):
-        return self.eng.read(L.F_CAM_BELIEF)[:, 27:]
+        return self.eng.read(L.F_CAM_MU)
 
     def lmk_means(self):
-        return self.eng.read(L.F_LMK_BELIEF)[:, 9:]
+        return self.eng.read(L.F_LMK_MU)
 
     def fill_iters(self, v):
         self.eng.fill_iters(v)

@@ -86,6 +86,8 @@ typedef enum gbp_field {
     GBP_F_ADJ = 12,         /* F x 2 int32 : (camera id, landmark id) = Factor.adj_vIDs (landmark NOT offset by C; read only) */
     GBP_F_FILE_INDEX = 13,  /* F x int32 : position of each factor in the measurement list passed to create (read only)    */
     GBP_F_CAM_PARTIAL = 14, /* C x 27 : this rank's sum of factor->keyframe messages (multi-GPU exchange buffer; read only) */
+    GBP_F_CAM_MU = 15,      /* C x 6 : compact copy of the keyframe means (VariableNode.mu, gbp/gbp.py:193; read only)     */
+    GBP_F_LMK_MU = 16,      /* L x 3 : compact copy of the landmark means (read only)                                      */
     GBP_F__COUNT
 } gbp_field;
 
@@ -145,10 +147,10 @@ int gbp_ba_update_beliefs(gbp_handle h);
 int gbp_ba_metrics(gbp_handle h, double out[3]);
 
 /* Snapshot = what the client of ba.py looks at between two sweeps (ba.py:95-103): the three numbers of
- * gbp_ba_metrics and both belief tables.  They are contiguous on the device, so a snapshot is ONE
- * device->host copy into a caller-owned PAGE-LOCKED region (gbp_host_alloc) of out[0] bytes with the
- * metrics at byte offset out[1], the keyframe rows (GBP_F_CAM_BELIEF layout) at out[2] and the landmark
- * rows at out[3]. */
+ * gbp_ba_metrics and the means of all variables (what the viewer draws).  They are contiguous on the
+ * device, so a snapshot is ONE small device->host copy into a caller-owned PAGE-LOCKED region
+ * (gbp_host_alloc) of out[0] bytes with the metrics at byte offset out[1], the keyframe means
+ * (GBP_F_CAM_MU, C x 6) at out[2] and the landmark means (GBP_F_LMK_MU, L x 3) at out[3]. */
 int gbp_ba_snapshot_layout(gbp_handle h, uint64_t out[4]);
 /* Enqueue metrics + copy behind the work already on the stream; no host synchronisation.  The region must
  * stay alive until gbp_ba_snapshot_wait returns. */
