@@ -55,6 +55,14 @@ def load_fr1desk():
     return prob, G
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def b_alg(F, L, C):
     """Algorithmic bytes of one synchronous iteration and of the sweep kernel alone."""
     total = 696 * F + 264 * L + 744 * C
@@ -215,7 +223,7 @@ def bench_ours(args):
     tot_ms, sweep_ms = eng.time_iterations(100, True, True, per_kernel=True)
     total_b, sweep_b = b_alg(F, Lm, C)
     roof_fr1 = {"bound": "hbm", "kernel": "sweep_kernel", "achieved": sweep_b / (sweep_ms / 100 * 1e-3) / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "traffic": None, "us_per_launch": sweep_ms / 100 * 1e3, "us_per_iteration": tot_ms / 100 * 1e3,
+                "unit": "GB/s", "traffic": ncu_traffic("sweep_kernel/fr1desk"), "us_per_launch": sweep_ms / 100 * 1e3, "us_per_iteration": tot_ms / 100 * 1e3,
                 "note": "10 MB working set is L2-resident: latency/launch-bound, HBM fraction is not meaningful here"}
     roof_fr1["frac"] = roof_fr1["achieved"] / hbm_peak
 
@@ -335,7 +343,9 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     if sweep_ms is not None:
         ach = sweep_b_local / (sweep_ms / k * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "sweep_kernel", "workload": synth["workload"], "achieved": ach, "peak": hbm_peak,
-                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "ms_per_launch": sweep_ms / k,
+                "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": ncu_traffic(f"sweep_kernel/synthetic_{C}_{Lm}_{F}"), "traffic_source": "profiles/traffic.json (ncu --set full, per launch)",
+                "ms_per_launch": sweep_ms / k,
                 "algorithmic_bytes_per_launch": sweep_b_local,
                 "how": "CUDA events around every sweep_kernel launch on the engine's stream (gbp_ba_time_iterations, per_kernel=1)"}
         synth["ms_per_iteration_eager_with_events"] = tot_ms / k
