@@ -19,7 +19,7 @@ ABI_VERSION = 1
  F_FLAGS, F_ADAPTIVE_VAR, F_MEASUREMENT, F_JACOBIAN_B, F_ADJ, F_FILE_INDEX, F_CAM_PARTIAL, F_CAM_MU, F_LMK_MU) = range(17)
 
 # stages
-ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING = 1, 2, 4, 8, 16
+ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
 
@@ -52,7 +52,7 @@ class GbpConfig(C.Structure):
 EXPORTS = [
     "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes",
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
-    "gbp_ba_sweep_local", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
+    "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
     "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
 ]
@@ -84,6 +84,7 @@ def load():
     lib.gbp_ba_set_priors.argtypes = [vp, vp, vp]
     lib.gbp_ba_scale_priors.argtypes = [vp, C.c_double]
     lib.gbp_ba_sweep_local.argtypes = [vp, C.c_int]
+    lib.gbp_ba_landmark_update.argtypes = [vp]
     lib.gbp_ba_cam_update.argtypes = [vp, vp, C.c_int]
     lib.gbp_ba_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.gbp_ba_update_beliefs.argtypes = [vp]

@@ -180,18 +180,18 @@ int launch_sweep(gbp_ba_graph* g, int stages) {
     }
 }
 
-// landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise)
-int launch_belief(gbp_ba_graph* g, int finalise) {
+// landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise); parts: bit0 keyframes, bit1 landmarks
+int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     BeliefParams p{};
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
-    p.L = g->L; p.C = g->C; p.finalise = finalise;
+    p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
     static const int lanes_override = getenv("GBP_LMK_LANES") ? atoi(getenv("GBP_LMK_LANES")) : 0;   // experiments only
     const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : 8);
     const int per_cta = 128 / lanes;
-    const int blocks = (g->L + per_cta - 1) / per_cta + (g->C + 3) / 4;
+    const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
     switch (lanes) {
         case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
@@ -591,8 +591,13 @@ int gbp_ba_sweep_local(gbp_handle h, int stages) {
         int rc = launch_sweep(h, stages);
         if (rc != GBP_OK) return rc;
     }
-    if (stages & ST_BELIEFS) return launch_belief(h, 0);
+    if (stages & ST_BELIEFS) return launch_belief(h, 0, (stages & GBP_STAGE_DEFER_LANDMARKS) ? 1 : 3);
     return GBP_OK;
+}
+
+int gbp_ba_landmark_update(gbp_handle h) {
+    CHECK_H(h);
+    return launch_belief(h, 0, 2);
 }
 
 int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {

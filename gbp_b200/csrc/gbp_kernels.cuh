@@ -424,6 +424,7 @@ struct BeliefParams {
     double* cam_mu;          // [C][6]  compact copy of the means (snapshot region)
     double* lmk_mu;          // [L][3]
     int L, C, finalise;
+    int parts;               // bit0: keyframe CTAs, bit1: landmark CTAs (multi-GPU runs them as two launches)
 };
 
 __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out) {
@@ -463,7 +464,7 @@ __device__ __forceinline__ void load_row9(const double* __restrict__ row, bool e
 template <int LMK_LANES>
 __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     constexpr int LMK_PER_CTA = 128 / LMK_LANES;
-    const int cam_blocks = (p.C + 3) / 4;
+    const int cam_blocks = (p.parts & 1) ? (p.C + 3) / 4 : 0;
     if ((int)blockIdx.x < cam_blocks) {
         // ---- keyframes first in the grid: their serial tile loops overlap the landmark CTAs
         const int c = (int)blockIdx.x * 4 + (threadIdx.x >> 5);

@@ -73,6 +73,9 @@ class CudaEngineAdapter:
     def sweep_local(self, stages):
         self.eng.sweep_local(stages)
 
+    def landmark_update(self):
+        self.eng.landmark_update()
+
     def partial_tensor(self):
         return self._partial
 
@@ -128,8 +131,12 @@ class PartitionedBAGraph:
 
     # ------------------------------------------------------------------ exchange
     def _exchange_and_update(self):
+        """keyframe partial sums -> all ranks (one all-gather); the landmark beliefs, which need no communication, are
+        updated on the compute stream while the collective is in flight; then prior + partials in rank order."""
         a = self.adapter
-        self.dist.all_gather_into_tensor(self._gather, a.partial_tensor())
+        work = self.dist.all_gather_into_tensor(self._gather, a.partial_tensor(), async_op=True)
+        a.landmark_update()
+        work.wait()
         a.apply_gathered(self._gather, self.world)
 
     # ------------------------------------------------------------------ API
@@ -152,7 +159,7 @@ class PartitionedBAGraph:
         if self.world == 1:
             self.adapter.update_beliefs_single()
         else:
-            self.adapter.sweep_local(L.ST_BELIEFS)
+            self.adapter.sweep_local(L.ST_BELIEFS | L.ST_DEFER_LANDMARKS)
             self._exchange_and_update()
 
     def synchronous_iteration(self, local_relin=True, robustify=False):
@@ -160,7 +167,7 @@ class PartitionedBAGraph:
         if self.world == 1:
             self.adapter.iterate_single(robustify, local_relin)
             return
-        st = L.ST_MESSAGES | L.ST_BELIEFS
+        st = L.ST_MESSAGES | L.ST_BELIEFS | L.ST_DEFER_LANDMARKS
         if robustify:
             st |= L.ST_ROBUSTIFY
         if local_relin:
@@ -179,7 +186,7 @@ class PartitionedBAGraph:
         if self.world == 1 or self._torch_stream is None:
             return False
         import torch
-        st = L.ST_MESSAGES | L.ST_BELIEFS | (L.ST_ROBUSTIFY if robustify else 0) | \
+        st = L.ST_MESSAGES | L.ST_BELIEFS | L.ST_DEFER_LANDMARKS | (L.ST_ROBUSTIFY if robustify else 0) | \
             ((L.ST_RELIN | L.ST_LOCAL_DAMPING) if local_relin else 0)
         if st in self._graphs:
             return True

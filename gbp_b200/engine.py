@@ -100,6 +100,9 @@ class BAEngine:
     def sweep_local(self, stages):
         L.check(self._lib.gbp_ba_sweep_local(self._h, int(stages)))
 
+    def landmark_update(self):
+        L.check(self._lib.gbp_ba_landmark_update(self._h))
+
     def cam_update(self, partials_dev_ptr=None, nranks=1):
         L.check(self._lib.gbp_ba_cam_update(self._h, C.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
                                             int(nranks)))

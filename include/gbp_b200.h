@@ -64,7 +64,9 @@ enum {
     GBP_STAGE_RELIN = 2,     /* relinearise_factors     gbp/gbp.py:64-80          */
     GBP_STAGE_MESSAGES = 4,  /* compute_all_messages    gbp/gbp.py:46-54, 334-373 */
     GBP_STAGE_BELIEFS = 8,   /* update_all_beliefs      gbp/gbp.py:56-58, 176-198 */
-    GBP_STAGE_LOCAL_DAMPING = 16 /* local_relin=True: per-factor damping (gbp/gbp.py:49-52) */
+    GBP_STAGE_LOCAL_DAMPING = 16, /* local_relin=True: per-factor damping (gbp/gbp.py:49-52) */
+    GBP_STAGE_DEFER_LANDMARKS = 32 /* with BELIEFS in gbp_ba_sweep_local: only reduce the keyframe partial sums; the
+                                      landmark beliefs are updated by gbp_ba_landmark_update (overlaps the exchange) */
 };
 
 /* Fields readable / writable through gbp_ba_read / gbp_ba_write.  Row widths in doubles
@@ -129,6 +131,9 @@ int gbp_ba_scale_priors(gbp_handle h, double factor);
  * sum of factor->keyframe messages is left in GBP_F_CAM_PARTIAL; keyframe beliefs are finalised by
  * gbp_ba_cam_update.  Everything is enqueued on the handle's stream; no host synchronisation. */
 int gbp_ba_sweep_local(gbp_handle h, int stages);
+/* The landmark half of update_all_beliefs (gbp/gbp.py:176-198) after a sweep with GBP_STAGE_DEFER_LANDMARKS: needs
+ * no communication, so a multi-GPU caller runs it while the keyframe partial sums are being exchanged. */
+int gbp_ba_landmark_update(gbp_handle h);
 /* Finish VariableNode.update_belief (gbp/gbp.py:176-198) for the keyframes: belief = prior + sum over
  * ranks (in rank order) of the partial sums.  `partials` is a DEVICE pointer to nranks x C x 27
  * doubles (e.g. the output of an NCCL all-gather of GBP_F_CAM_PARTIAL); NULL = use this handle's own

@@ -57,10 +57,15 @@ class OracleAdapter:
             ce = np.zeros((o.C, 6)); cl = np.zeros((o.C, 6, 6))
             np.add.at(ce, o.cam, o.msg_cam_eta); np.add.at(cl, o.cam, o.msg_cam_lam)
             self._partial.copy_(torch.from_numpy(np.concatenate([ce, cl[:, IU6[0], IU6[1]]], axis=1).ravel()))
-            le = o.lmk_prior_eta.copy(); ll = o.lmk_prior_lam.copy()
-            np.add.at(le, o.lmk, o.msg_lmk_eta); np.add.at(ll, o.lmk, o.msg_lmk_lam)
-            o.lmk_eta, o.lmk_lam = le, ll
-            o.lmk_mu = np.einsum("vij,vj->vi", np.linalg.inv(ll), le)
+            if not stages & L.ST_DEFER_LANDMARKS:
+                self.landmark_update()
+
+    def landmark_update(self):
+        o = self.o
+        le = o.lmk_prior_eta.copy(); ll = o.lmk_prior_lam.copy()
+        np.add.at(le, o.lmk, o.msg_lmk_eta); np.add.at(ll, o.lmk, o.msg_lmk_lam)
+        o.lmk_eta, o.lmk_lam = le, ll
+        o.lmk_mu = np.einsum("vij,vj->vi", np.linalg.inv(ll), le)
 
     def partial_tensor(self):
         return self._partial
