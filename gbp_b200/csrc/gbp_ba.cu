@@ -146,7 +146,19 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
     const SweepParams p = sweep_params(g, stages);
     constexpr size_t smem = sweep_smem_bytes<T>();
     static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
-    if (g->cfg.kernel_variant == 1) {   // first-version kernel (cooperative LDG/STS staging), for A/B measurements
+    if (g->cfg.kernel_variant == 4 && T <= 64) {   // persistent double-buffered kernel
+        constexpr size_t psmem = sweep_persistent_smem_bytes<(T <= 64 ? T : 64)>();
+        static_assert(psmem <= 48 * 1024, "persistent sweep stages must fit the default dynamic shared memory limit");
+        int sms = 148, per_sm = 4;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+        if (g->robust) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel_persistent<(T <= 64 ? T : 64), true>, T, psmem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel_persistent<(T <= 64 ? T : 64), false>, T, psmem);
+        const int grid = std::min(g->n_tiles, std::max(1, per_sm) * sms);
+        if (g->robust)
+            sweep_kernel_persistent<(T <= 64 ? T : 64), true><<<grid, T, psmem, g->stream>>>(p);
+        else
+            sweep_kernel_persistent<(T <= 64 ? T : 64), false><<<grid, T, psmem, g->stream>>>(p);
+    } else if (g->cfg.kernel_variant == 1) {   // first-version kernel (cooperative LDG/STS staging), for A/B measurements
         if (g->robust)
             sweep_kernel_ldg<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
         else

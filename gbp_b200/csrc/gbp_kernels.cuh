@@ -76,11 +76,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "GBP_WAIT:\n\t"
+        "GBP_WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra GBP_DONE;\n\t"
-        "bra GBP_WAIT;\n\t"
-        "GBP_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "@P1 bra GBP_DONE_%=;\n\t"
+        "bra GBP_WAIT_%=;\n\t"
+        "GBP_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
@@ -359,6 +359,97 @@ __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const
     if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
 }
 
+// ----------------------------------------------------------------------------------------
+// Persistent, double-buffered variant (kernel_variant 4): a CTA walks tiles blockIdx.x, +gridDim.x, ... and
+// while it computes tile i from stage s it already has tile i+1 in flight into stage s^1 (bulk copies on
+// that stage's mbarrier; the per-edge scalars and the gathered landmark belief row wait in registers).
+// Fewer resident warps (8 per SM instead of 12: 216 registers, two stages of shared memory), but none of them
+// ever waits for its tile.  MEASURED SLOWER (1.38 vs 1.18 ms on the 10 M-factor graph): with 8 warps the SM is
+// bound by the latency of the dependent fp64 chains, not by memory.  Kept for A/B runs only.
+// ----------------------------------------------------------------------------------------
+template <int T>
+constexpr size_t sweep_persistent_smem_bytes() {
+    return sizeof(double) * (size_t)(2 * T * (CAM_M + LMK_M + 9) + 2 * 34 + (T / 32) * CAM_M + 2 /* two mbarriers */);
+}
+
+template <int T, bool ROBUST>
+__global__ void __launch_bounds__(T, 256 / T) sweep_kernel_persistent(const SweepParams p) {
+    extern __shared__ __align__(128) double smem[];
+    constexpr int STAGE = T * (CAM_M + LMK_M + 9);
+    double* s_cb = smem + 2 * STAGE;         // [2][34]
+    double* s_red = s_cb + 2 * 34;           // [T/32][27]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);   // [2]
+    const int tid = threadIdx.x;
+    int tile = blockIdx.x;
+    if (tile >= p.n_tiles) return;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+    }
+    __syncthreads();
+    const uint64_t pol = policy_evict_first();
+
+    auto issue = [&](int t, const Tile& tl, int s) {   // thread 0: bulk loads of tile t into stage s
+        double* st = smem + s * STAGE;
+        const long long base = (long long)t * T;
+        const uint32_t n_even = (uint32_t)((tl.count + 1) & ~1);
+        mbar_expect_tx(&bar[s], n_even * (CAM_M + LMK_M + 9) * 8);
+        bulk_g2s_hint(st, p.msg_cam + base * CAM_M, n_even * CAM_M * 8, &bar[s], pol);
+        bulk_g2s_hint(st + T * CAM_M, p.msg_lmk + base * LMK_M, n_even * LMK_M * 8, &bar[s], pol);
+        bulk_g2s_hint(st + T * (CAM_M + LMK_M), p.linpoint + base * 9, n_even * 72, &bar[s], pol);
+    };
+
+    Tile tl_cur = p.tiles[tile];
+    EdgeRegs r_cur;
+    if (tid == 0) issue(tile, tl_cur, 0);
+    if (tid < tl_cur.count) load_edge_regs<true>(p, (long long)tile * T + tid, r_cur);
+    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl_cur.cam * CAM_B + i];
+
+    for (int it = 0;; ++it) {
+        const int s = it & 1;
+        const int next = tile + (int)gridDim.x;
+        const bool has_next = next < p.n_tiles;
+        Tile tl_next = tl_cur;
+        EdgeRegs r_next;
+        if (has_next) {
+            tl_next = p.tiles[next];
+            if (tid == 0) {
+                bulk_wait_read0();             // the stores of tile it-1 have finished reading stage s^1
+                issue(next, tl_next, s ^ 1);
+            }
+            if (tid < tl_next.count) load_edge_regs<true>(p, (long long)next * T + tid, r_next);
+            for (int i = tid; i < CAM_B; i += T) s_cb[(s ^ 1) * 34 + i] = p.cam_belief[(long long)tl_next.cam * CAM_B + i];
+        }
+        __syncthreads();                        // s_cb[s] (written one iteration ago) visible to everyone
+        mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
+
+        double* s_mc = smem + s * STAGE;
+        double* s_ml = s_mc + T * CAM_M;
+        double* s_lp = s_ml + T * LMK_M;
+        const int n = tl_cur.count;
+        const long long base = (long long)tile * T;
+        bool relin = false;
+        if (tid < n) relin = edge_sweep<ROBUST>(p, base + tid, r_cur, s_cb + s * 34, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
+        fence_async_smem();
+        const int any_relin = __syncthreads_or(relin ? 1 : 0);
+        if (tid == 0) {
+            const uint32_t n_even = (uint32_t)((n + 1) & ~1);
+            if (p.stages & ST_MESSAGES) {
+                bulk_s2g_hint(p.msg_cam + base * CAM_M, s_mc, n_even * CAM_M * 8, pol);
+                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, n_even * LMK_M * 8);
+            }
+            if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, n_even * 72, pol);
+            bulk_commit();
+        }
+        if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
+        if (!has_next) break;
+        tile = next;
+        tl_cur = tl_next;
+        r_cur = r_next;
+    }
+    if (tid == 0) bulk_wait_read0();
+}
+
 template <int T, bool ROBUST>
 __global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
@@ -498,7 +589,21 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     for (int k = 0; k < LMK_M; ++k) acc[k] = 0.0;
     if (valid) {
         const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
-        for (int q = p0 + sub; q < p1; q += LMK_LANES) {
+        int q = p0 + sub;
+        // four rows in flight per thread (slot loads, then row loads, then the adds in edge order)
+        for (; q + 3 * LMK_LANES < p1; q += 4 * LMK_LANES) {
+            int slot[4];
+            double v[4][9];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) slot[u] = p.lmk_slots[q + u * LMK_LANES];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load_row9(p.msg_lmk + (long long)slot[u] * LMK_M, (slot[u] & 1) == 0, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < LMK_M; ++k) acc[k] += v[u][k];
+        }
+        for (; q < p1; q += LMK_LANES) {
             const int slot = p.lmk_slots[q];
             double v[9];
             load_row9(p.msg_lmk + (long long)slot * LMK_M, (slot & 1) == 0, v);

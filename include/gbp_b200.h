@@ -55,7 +55,8 @@ typedef struct gbp_config {
     int32_t loss;                /* gbp_loss (gbp/gbp.py:243)                                  */
     int32_t tile_edges;          /* 0 = auto; else 32/64/128 edges per tile (engine tuning)    */
     int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
-    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default); 1 = first-version LDG kernel; 2 = TMA, no hints */
+    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default); 1 = first-version LDG kernel; 2 = TMA, no hints;
+                                    3 = 128-register build; 4 = persistent double-buffered (tiles of 32 / 64) */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */

@@ -181,14 +181,20 @@ def test_kernel_variants_agree():
     from gbp_b200.ba import create_ba_graph
     from gbp_b200 import _lib as L
     G = load_golden("fr1desk_vsmall_huber")
-    gs = [create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=t, kernel_variant=v) for t, v in ((64, 0), (64, 1), (128, 0))]
+    gs = [create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=t, kernel_variant=v)
+          for t, v in ((64, 0), (64, 1), (128, 0), (64, 2), (64, 3), (64, 4), (32, 4))]
     for g in gs:
         g.generate_priors_var(50.0)
         g.update_all_beliefs()
         g.iterate(8); g._eng.fill_iters(8); g.iterate(12, robustify=True)
     for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ADAPTIVE_VAR, L.F_ITERS, L.F_FLAGS):
-        assert np.array_equal(gs[0]._eng.read(f), gs[1]._eng.read(f)), f
+        for k in (1, 3, 4, 5):      # same tile size: same arithmetic in the same order (variant 3 may contract differently)
+            if k == 4:
+                assert relerr(gs[k]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, (f, k)
+            else:
+                assert np.array_equal(gs[0]._eng.read(f), gs[k]._eng.read(f)), (f, k)
         assert relerr(gs[2]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, f
+        assert relerr(gs[6]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, f
     for g in gs:
         g.close()
 
