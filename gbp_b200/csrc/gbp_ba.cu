@@ -297,14 +297,20 @@ void* field_dev_ptr(gbp_ba_graph* g, int field) {
     }
 }
 
-int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out) {
-    auto it = g->graphs.find(stages);
+// CUDA graph of `reps` consecutive iterations [sweep, beliefs] x reps (fewer, longer launches: the gap between two
+// graph launches is larger than the gap between two nodes of one graph, which matters at 10 us per iteration)
+int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
+    const int key = stages | (reps << 8);
+    auto it = g->graphs.find(key);
     if (it != g->graphs.end()) { *out = it->second; return GBP_OK; }
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     const long long before = g->launches;
-    int rc = launch_sweep(g, stages);
-    if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1);
+    int rc = GBP_OK;
+    for (int r = 0; r < reps && rc == GBP_OK; ++r) {
+        rc = launch_sweep(g, stages);
+        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1);
+    }
     g->launches = before;  // capture does not execute
     cudaError_t e = cudaStreamEndCapture(g->stream, &graph);
     if (rc != GBP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -313,7 +319,7 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out) {
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-    g->graphs[stages] = exec;
+    g->graphs[key] = exec;
     *out = exec;
     return GBP_OK;
 }
@@ -629,11 +635,21 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (n_iters < 0) return fail(GBP_ERR_INVALID, "n_iters < 0");
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
-    cudaGraphExec_t exec;
-    int rc = get_graph(h, st, &exec);
-    if (rc != GBP_OK) return rc;
+    constexpr int REPS = 8;
     const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
-    for (int i = 0; i < n_iters; ++i) CU(cudaGraphLaunch(exec, h->stream));
+    int left = n_iters;
+    if (left >= REPS) {
+        cudaGraphExec_t exec8;
+        int rc = get_graph(h, st, &exec8, REPS);
+        if (rc != GBP_OK) return rc;
+        for (; left >= REPS; left -= REPS) CU(cudaGraphLaunch(exec8, h->stream));
+    }
+    if (left > 0) {
+        cudaGraphExec_t exec;
+        int rc = get_graph(h, st, &exec);
+        if (rc != GBP_OK) return rc;
+        for (; left > 0; --left) CU(cudaGraphLaunch(exec, h->stream));
+    }
     h->launches += (long long)per_iter * n_iters;
     return GBP_OK;
 }

@@ -126,6 +126,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // per-edge register inputs fetched straight from global memory
 struct EdgeRegs {
     int it, fl;
+    double var;         // adaptive variance (robust losses only), prefetched with the other scalars
     double z[2];
     double bl[LMK_B];   // landmark belief row (gathered)
 };
@@ -135,6 +136,7 @@ __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e
     const int lmk = p.lmk_idx[e];
     r.it = p.iters[e];
     r.fl = p.flags[e];
+    r.var = (p.loss != 0) ? p.sigma2a[e] : p.var0;
     const double2 zz = reinterpret_cast<const double2*>(p.z)[e];
     r.z[0] = zz.x;
     r.z[1] = zz.y;
@@ -183,7 +185,7 @@ __device__ __forceinline__ bool edge_sweep(const SweepParams& p, long long e, Ed
     double J[18], h0[2];
     bool lin_done = false;
     if (ROBUST) {
-        var = p.sigma2a[e];
+        var = r.var;
         if (p.stages & ST_ROBUSTIFY) {
             // robustify_loss uses h at the STORED linearisation point (gbp/gbp.py:309-312)
             double r0, r1;

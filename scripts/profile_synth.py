@@ -20,8 +20,9 @@ ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--fr1desk", action="store_true")
 ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--loss", default=None)
 a = ap.parse_args()
-cfg = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
+cfg = dict(gauss_noise_std=2, loss=a.loss, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
 if a.fr1desk:
     import numpy as np
     from gbp_b200 import balio
@@ -39,7 +40,9 @@ for i in range(a.iters):                      # eager launches (one sweep_kernel
 e.synchronize()
 tot, sw = e.time_iterations(a.iters, True, True, per_kernel=True)
 tot_g, _ = e.time_iterations(a.iters, True, True, per_kernel=False)
+import time as _t
+e.synchronize(); _t0 = _t.perf_counter(); e.iterate(200, True, True); e.synchronize(); it200 = (_t.perf_counter() - _t0) / 200 * 1e3
 F, L, C = e.F, e.L, e.C
-print(f"variant={a.variant} F={F} L={L} C={C} tiles={e.n_tiles}x{e.tile_edges}  sweep {sw / a.iters:.4f} ms  iteration eager {tot / a.iters:.4f} ms  graph {tot_g / a.iters:.4f} ms"
+print(f"variant={a.variant} F={F} L={L} C={C} tiles={e.n_tiles}x{e.tile_edges}  sweep {sw / a.iters:.4f} ms  iteration eager {tot / a.iters:.4f} ms  graph {tot_g / a.iters:.4f} ms  iterate(200) wall {it200:.4f} ms/iter"
       f"  sweep GB/s {(696 * F + 96 * L + 264 * C) / (sw / a.iters * 1e-3) / 1e9:.1f}  iter GB/s {(696 * F + 264 * L + 744 * C) / (tot_g / a.iters * 1e-3) / 1e9:.1f}"
       f"  ARE {g.are():.4f}")
