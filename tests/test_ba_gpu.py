@@ -439,3 +439,26 @@ def test_full_size_properties():
     a1, a2 = g.are(), h.are()
     assert abs(a1 - a2) < 1e-9 * a1 and a1 < 5.0
     g.close(); h.close()
+
+
+def test_synthetic_small_against_reference_fixture():
+    """BASELINE configs 4-5 are pinned on a down-scaled instance of the same generator: the unmodified reference
+    ran `make_synthetic(20, 2000, 10, seed=0)` for 30 iterations (tests/golden/synth_small.npz)."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.synthetic import make_synthetic
+    G = load_golden("synth_small")
+    prob = make_synthetic(20, 2000, 10, seed=0)
+    ref = golden_problem(G)
+    for k in ("cam_id", "lmk_id", "z", "cam_means", "lmk_means", "K4"):      # the generator is deterministic
+        assert np.array_equal(getattr(prob, k), getattr(ref, k)), k
+    graph = create_ba_graph(prob, golden_configs(G), tile_edges=64, lmk_block=700)
+    cks = set(G["checkpoints"].tolist())
+
+    def on_iter(i):
+        if i in cks:
+            _check_snapshot(graph, G, f"s{i}", TOL_EARLY if i <= 1 else 1e-5)
+
+    are, en, nrel = _run_loop(graph, G, int(G["n_iters"]), on_iter)
+    assert np.array_equal(nrel, G["n_relin"])
+    assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
+    graph.close()

@@ -79,3 +79,21 @@ def test_fr1desk_trace_prefix():
     assert np.array_equal(nrel, G["n_relin"][:19])
     assert relerr(are, G["are"][:19]) < 1e-6 and relerr(en, G["energy"][:19]) < 1e-6
     assert relerr(o.cam_mu.ravel(), G["s16_cam_mu"]) > 0  # later sweep than the checkpoint: sanity of indexing
+
+
+def test_synthetic_small_trajectory():
+    """The oracle against the reference on the down-scaled synthetic problem (configs 4-5)."""
+    G = load_golden("synth_small")
+    o, cfg = make_oracle(G)
+    cks = set(G["checkpoints"].tolist())
+    worst = {}
+
+    def on_iter(i, o):
+        if i in cks:
+            worst[i] = max(relerr(o.cam_mu.ravel(), G[f"s{i}_cam_mu"]), relerr(o.lmk_mu.ravel(), G[f"s{i}_lmk_mu"]),
+                           relerr(o.cam_lam.ravel(), G[f"s{i}_cam_lam"]), relerr(o.lmk_lam.ravel(), G[f"s{i}_lmk_lam"]))
+            assert np.array_equal(o.iters_since_relin, G[f"s{i}_iters_since_relin"])
+
+    are, en, nrel = O.run_ba_loop(o, int(G["n_iters"]), cfg["prior_std_weaker_factor"], on_iter=on_iter)
+    assert np.array_equal(nrel, G["n_relin"])
+    assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6 and max(worst.values()) < 1e-5, worst
