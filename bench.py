@@ -327,6 +327,11 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     launches = pg.engine.launch_count() - l0
     t = max_over_ranks(e0.elapsed_time(e1) / 1e3)
     barrier()
+    are, energy, nrel = pg.metrics()
+    total_b, _ = b_alg(F, Lm, C)
+    eng = pg.engine
+    _, sweep_b_local = b_alg(eng.F, eng.L, eng.C)
+    tot_ms, sweep_ms = eng.time_iterations(k, True, True, per_kernel=True) if world == 1 else (None, None)
     # sustained: 200 back-to-back iterations (~0.3 s of continuous fp64 + HBM load; the burst above is ~30 ms)
     ks = args.synth_sustained
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,11 +342,6 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     torch.cuda.synchronize()
     t_sus = max_over_ranks(s0.elapsed_time(s1) / 1e3)
     barrier()
-    are, energy, nrel = pg.metrics()
-    total_b, _ = b_alg(F, Lm, C)
-    eng = pg.engine
-    _, sweep_b_local = b_alg(eng.F, eng.L, eng.C)
-    tot_ms, sweep_ms = eng.time_iterations(k, True, True, per_kernel=True) if world == 1 else (None, None)
     synth = {"workload": f"synthetic BAL {C} keyframes / {Lm} landmarks / {F} factors, {'landmark-partitioned over %d GPUs, one NCCL all-gather of keyframe partial sums per iteration' % world if world > 1 else '1 GPU'}",
              "value": k * 2 * F / t, "unit": UNIT, "ms_per_iteration": 1e3 * t / k, "iterations_timed": k, "scaling": "strong",
              "algorithmic_bytes_per_iteration": total_b, "achieved_gbs_whole_iteration_per_gpu": total_b / world / (t / k) / 1e9,
