@@ -17,8 +17,8 @@ The same run also measures the synthetic 1k-camera / 1M-landmark / 10M-factor gr
 meaningful: `roofline` refers to the sweep kernel on that graph, `roofline_fr1desk` to the
 (latency-bound, L2-resident) headline graph.
 
-``--impl reference`` times the CPU restatement of the reference algorithm (oracle/, NumPy; the
-Python reference itself cannot travel to the GPU box) on the same workload, a bounded sample per step.
+``--impl reference`` times the CPU restatement of the reference algorithm (oracle/gbp_oracle.c: plain C +
+OpenMP on every host thread; the Python reference itself cannot travel to the GPU box) on the same workload.
 """
 import argparse
 import json
@@ -366,56 +366,71 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     return synth, roof
 
 
-def cpu_baseline_sample(n_sweeps):
-    """The oracle (NumPy port of the reference algorithm) timed on the host, bounded sample."""
-    from oracle.gbp_oracle import BAOracle
-    prob, _ = load_fr1desk()
-    o = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
-    o.generate_priors_var(CFG["prior_std_weaker_factor"])
-    o.update_all_beliefs()
-    o.synchronous_iteration(robustify=True, local_relin=True)
-    t0 = time.perf_counter()
-    for i in range(n_sweeps):
-        if i == 3 or i == 8:
-            o.iters_since_relin[:] = 1
-        o.synchronous_iteration(robustify=True, local_relin=True)
-    dt = time.perf_counter() - t0
-    return {"value": n_sweeps * 2 * o.F / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n_sweeps} synchronous iterations of fr1desk by oracle/gbp_oracle.py (vectorised NumPy float64), {dt:.1f} s",
-            "host_cpus": os.cpu_count(),
-            "reference_measured_in_build_container": {"value": 7780.0, "unit": UNIT, "cores": 1,
-                                                      "source": "BASELINE.md: unmodified reference, 3.419 s per iteration on fr1desk"}}
-
-
-def bench_reference(args):
-    """Reference arm: the CPU restatement of the reference algorithm on the same workload."""
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    from oracle.gbp_oracle import BAOracle
-    prob, _ = load_fr1desk()
-    sweeps = args.ref_sweeps
-    times = []
-    for it in range(args.warmup + args.steps):
-        o = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
+def _c_oracle_solves(n_solves, threads):
+    """n_solves complete 200-iteration fr1desk solves by the plain-C OpenMP port of the reference algorithm."""
+    from oracle import c_oracle
+    c_oracle.set_threads(threads)
+    prob, G = load_fr1desk()
+    times, o = [], None
+    for _ in range(n_solves):
+        o = c_oracle.COracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
         o.generate_priors_var(CFG["prior_std_weaker_factor"])
         o.update_all_beliefs()
         t0 = time.perf_counter()
-        for i in range(sweeps):
+        for i in range(N_ITERS):
             if i == 3 or i == 8:
-                o.iters_since_relin[:] = 1
+                o.fill_iters(1)
             o.synchronous_iteration(robustify=True, local_relin=True)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-    msgs = sweeps * 2 * o.F
+        times.append(time.perf_counter() - t0)
+    mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
+    mu = np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])
+    return times, o, float(np.max(np.abs(mu - mu_ref)) / np.max(np.abs(mu_ref)))
+
+
+def cpu_baseline_sample(n_sweeps):
+    """CPU baseline on the GPU box's host cores: the plain-C OpenMP port (oracle/gbp_oracle.c) on all threads, plus
+    the single-threaded NumPy port for reference."""
+    from oracle.gbp_oracle import BAOracle
+    threads = os.cpu_count() or 1
+    times, o, err = _c_oracle_solves(12, threads)
+    times = times[2:]
+    c_val = len(times) * N_ITERS * 2 * o.F / float(np.sum(times))
+    prob, _ = load_fr1desk()
+    n = BAOracle(prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
+    n.generate_priors_var(CFG["prior_std_weaker_factor"])
+    n.update_all_beliefs()
+    n.synchronous_iteration(robustify=True, local_relin=True)
+    t0 = time.perf_counter()
+    for i in range(n_sweeps):
+        n.synchronous_iteration(robustify=True, local_relin=True)
+    dt = time.perf_counter() - t0
+    return {"value": c_val, "unit": UNIT, "cores": o.threads, "kind": "port",
+            "sample": f"{len(times)} complete 200-iteration fr1desk solves by oracle/gbp_oracle.c (plain C + OpenMP, reference arithmetic form), {float(np.sum(times)):.1f} s; means {err:.1e} from the reference fixture",
+            "host_cpus": os.cpu_count(),
+            "numpy_port_1_core": {"value": n_sweeps * 2 * n.F / dt, "unit": UNIT, "sample": f"{n_sweeps} iterations by oracle/gbp_oracle.py"},
+            "reference_measured_in_build_container": {"value": 7780.0, "unit": UNIT, "cores": 1,
+                                                      "source": "BASELINE.md: unmodified Python reference, 3.419 s per iteration on fr1desk"}}
+
+
+def bench_reference(args):
+    """Reference arm: the reference's algorithm on the host cores.  The Python reference cannot travel to the GPU box, so
+    this times the plain-C OpenMP port of it (oracle/gbp_oracle.c, pinned against the reference's fixtures) with every
+    host thread, one complete 200-iteration fr1desk solve per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times, o, err = _c_oracle_solves(args.warmup + args.steps, threads)
+    times = times[args.warmup:]
+    msgs = N_ITERS * 2 * o.F
     value = args.steps * msgs / float(np.sum(times))
-    sample = f"first {sweeps} of the 200 synchronous iterations of fr1desk per step, oracle/gbp_oracle.py (NumPy float64 port; the Python reference cannot travel to the GPU box)"
+    sample = f"one complete 200-iteration fr1desk solve per step by oracle/gbp_oracle.c (plain C + OpenMP port of the reference algorithm, {o.threads} threads)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "fr1desk measurements from the committed fixture",
-            "config": {"workload": WORKLOAD, "step": sample, "msgs_per_step": msgs},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()},
+            "config": {"workload": WORKLOAD, "step": "one 200-iteration solve from the initial state", "msgs_per_step": msgs},
+            "parity": {"max_rel_err_means_vs_reference_fixture": err},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.threads, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -433,8 +448,7 @@ def main():
     ap.add_argument("--synth-lmks", type=int, default=1_000_000)
     ap.add_argument("--synth-iters", type=int, default=20)
     ap.add_argument("--synth-sustained", type=int, default=200)
-    ap.add_argument("--cpu-sweeps", type=int, default=200)
-    ap.add_argument("--ref-sweeps", type=int, default=25)
+    ap.add_argument("--cpu-sweeps", type=int, default=40, help="NumPy-port iterations timed for the secondary CPU figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
