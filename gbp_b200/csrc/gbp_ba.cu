@@ -201,7 +201,8 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
     static const int lanes_override = getenv("GBP_LMK_LANES") ? atoi(getenv("GBP_LMK_LANES")) : 0;   // experiments only
-    const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : 8);
+    // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds
+    const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : (g->L > 8192 ? 8 : 32));
     const int per_cta = 128 / lanes;
     const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
@@ -209,6 +210,7 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
         case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
         case 2: belief_kernel<2><<<blocks, 128, 0, g->stream>>>(p); break;
         case 4: belief_kernel<4><<<blocks, 128, 0, g->stream>>>(p); break;
+        case 32: belief_kernel<32><<<blocks, 128, 0, g->stream>>>(p); break;
         default: belief_kernel<8><<<blocks, 128, 0, g->stream>>>(p); break;
     }
     g->launches++;

@@ -552,8 +552,8 @@ __device__ __forceinline__ void load_row9(const double* __restrict__ row, bool e
     }
 }
 
-// LMK_LANES lanes cooperate on one landmark: 8 for small graphs (latency: a landmark of degree 46 is
-// gathered in 6 rounds instead of 46), 1-2 for large ones (throughput: full lanes in the 3x3 solve).
+// LMK_LANES lanes cooperate on one landmark: 32 / 8 for small / medium graphs (latency: a landmark of degree 46
+// is gathered in 2 / 6 dependent rounds instead of 46), 1-2 for large ones (throughput: full lanes in the 3x3 solve).
 template <int LMK_LANES>
 __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     constexpr int LMK_PER_CTA = 128 / LMK_LANES;
