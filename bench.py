@@ -9,9 +9,11 @@ synchronous iterations.  One STEP = one complete 200-iteration solve from the in
 the graph state is reset and L2 is flushed between steps (both untimed), inside a step the
 10 MB working set is legitimately L2-resident, as in a real run.
   value  = GBP messages/s = 200 * 2F / device time of the step (CUDA events on the engine's stream)
-  e2e    = the same metric through the public Python API starting from HOST arrays: graph build +
-           upload, priors, 200 x (metrics read-back, belief means read-back like the viewer,
-           synchronous_iteration), final means on the host; wall clock with synchronisation.
+  e2e    = the same step through the public Python API starting from pinned HOST arrays: create_ba_graph
+           (graph compile + upload), priors, the 200 synchronous iterations with the two resets, final
+           means read back to the host; wall clock with synchronisation.  `e2e_client_loop` is the same
+           solve driven exactly like ba.py's loop body (are / energy / relinearisation count and the
+           viewer's means read back to the host between every two sweeps).
 The same run also measures the synthetic 1k-camera / 1M-landmark / 10M-factor graph (configs[3];
 7.2 GB of state streamed per iteration, far larger than L2), which is where the HBM roofline is
 meaningful: `roofline` refers to the sweep kernel on that graph, `roofline_fr1desk` to the
@@ -125,11 +127,21 @@ def solve_200(graph):
     e.iterate(N_ITERS - 8, robustify=True, local_relin=True)
 
 
+def solve_api(graph):
+    """The sweep schedule of ba.py:84-105 through the public graph API, no per-iteration host reads."""
+    graph.iterate(3, robustify=True, local_relin=True)
+    graph.reset_iters_since_relin(1)               # ba.py:91-93 at i = 3
+    graph.iterate(5, robustify=True, local_relin=True)
+    graph.reset_iters_since_relin(1)               # ... and at i = 8
+    graph.iterate(N_ITERS - 8, robustify=True, local_relin=True)
+    return graph.get_means()
+
+
 def client_loop(graph):
     """The loop body of ba.py:84-105 through the public API (metrics + viewer reads every iteration)."""
     for i in range(N_ITERS):
         if i == 3 or i == 8:
-            graph._flush(); graph._eng.fill_iters(1); graph._invalidate((7,))
+            graph.reset_iters_since_relin(1)
         graph.metrics()                    # are(), energy(), relinearisation count  (ba.py:95-100)
         graph.cam_nodes[0].mu; graph.lmk_nodes[0].mu     # viewer.update reads the means (ba.py:103)
         graph.synchronous_iteration(robustify=True, local_relin=True)
@@ -230,29 +242,39 @@ def bench_ours(args):
     # ------------------------------------------------------------------ e2e through the public API
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
               for k, v in dict(cam_id=prob.cam_id, lmk_id=prob.lmk_id, z=prob.z, cam=prob.cam_means, lmk=prob.lmk_means).items()}
-    h2d = sum(v.nbytes for v in pinned.values())
-    d2h = N_ITERS * (24 + (C * 33 + Lm * 12) * 8) + (6 * C + 3 * Lm) * 8
-    e2e_s = []
-    for it in range(args.warmup + args.steps):
-        flush_buf.zero_(); barrier()
-        t0 = time.perf_counter()
-        p2 = balio.BALProblem(pinned["cam_id"], pinned["lmk_id"], pinned["z"], pinned["cam"], pinned["lmk"], prob.K4)
-        g2 = create_ba_graph(p2, CFG, device=local, stream=stream)
-        t1 = time.perf_counter()
-        g2.generate_priors_var(weaker_factor=CFG["prior_std_weaker_factor"])
-        g2.update_all_beliefs()
-        t2 = time.perf_counter()
-        means = client_loop(g2)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if os.environ.get("GBP_BENCH_DEBUG"):
-            print(f"[e2e {it}] create {1e3 * (t1 - t0):.2f} ms  priors {1e3 * (t2 - t1):.2f}  loop {1e3 * (t0 + dt - t2):.2f}  total {1e3 * dt:.2f}", file=sys.stderr)
-        g2.close()
-        if it >= args.warmup:
-            e2e_s.append(dt)
-    e2e_t = max_over_ranks(float(np.sum(e2e_s)))
+    snap_bytes = eng.snapshot_layout()[0]
+    # bytes the engine really moves: the compiled graph (slot-ordered ids + measurements, tiles, both CSR tables) and
+    # the initial means go up; every snapshot (metrics + compact means) comes down
+    h2d = eng.n_slots * (4 + 16) + eng.n_tiles * (8 + 4) + F * (4 + 4) + (Lm + 1) * 4 + (C + 1) * 4 + (6 * C + 3 * Lm) * 8
+
+    def e2e_run(loop, tag):
+        times, means = [], None
+        for it in range(args.warmup + args.steps):
+            flush_buf.zero_(); barrier()
+            t0 = time.perf_counter()
+            p2 = balio.BALProblem(pinned["cam_id"], pinned["lmk_id"], pinned["z"], pinned["cam"], pinned["lmk"], prob.K4)
+            g2 = create_ba_graph(p2, CFG, device=local, stream=stream)
+            t1 = time.perf_counter()
+            g2.generate_priors_var(weaker_factor=CFG["prior_std_weaker_factor"])
+            g2.update_all_beliefs()
+            t2 = time.perf_counter()
+            means = loop(g2)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if os.environ.get("GBP_BENCH_DEBUG"):
+                print(f"[{tag} {it}] create {1e3 * (t1 - t0):.2f} ms  priors {1e3 * (t2 - t1):.2f}  loop {1e3 * (t0 + dt - t2):.2f}  total {1e3 * dt:.2f}", file=sys.stderr)
+            g2.close()
+            if it >= args.warmup:
+                times.append(dt)
+        t = max_over_ranks(float(np.sum(times)))
+        return t, float(np.max(np.abs(means - mu_ref)) / np.max(np.abs(mu_ref)))
+
+    e2e_t, e2e_parity = e2e_run(solve_api, "e2e")
     e2e_val = world * args.steps * msgs_per_step / e2e_t
-    e2e_parity = float(np.max(np.abs(means - mu_ref)) / np.max(np.abs(mu_ref)))
+    d2h = 3 * snap_bytes                             # one snapshot behind each of the three iterate() calls
+    loop_t, loop_parity = e2e_run(client_loop, "e2e_client_loop")
+    loop_val = world * args.steps * msgs_per_step / loop_t
+    d2h_loop = (N_ITERS + 1) * snap_bytes
     graph.close()
 
     # ------------------------------------------------------------------ synthetic 10M-factor graph
@@ -281,10 +303,13 @@ def bench_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_t / args.steps,
-                    "what": "create_ba_graph from pinned host arrays + priors + 200 x (metrics, means read-back, synchronous_iteration) + final means"},
+                    "what": "create_ba_graph from pinned host arrays (graph compile + upload) + priors + 200 synchronous iterations with the resets at 3 and 8 + final means on the host; wall clock"},
+            "e2e_client_loop": {"value": loop_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_loop,
+                                "ms_per_step": 1e3 * loop_t / args.steps, "max_rel_err": loop_parity,
+                                "what": "the same solve driven like ba.py's loop body: 200 x (are, energy, relinearisation count and the viewer's means read back to the host, synchronous_iteration); a serial CPU<->GPU ping-pong"},
             "gpu_launches": launches,
             "parity": {"max_rel_err_means_vs_reference_fixture": parity_mu, "e2e_max_rel_err": e2e_parity, "tol": 1e-4,
-                       "ok": bool(parity_mu < 1e-4 and e2e_parity < 1e-4), "final_are_px": are_final},
+                       "ok": bool(parity_mu < 1e-4 and e2e_parity < 1e-4 and loop_parity < 1e-4), "final_are_px": are_final},
             "roofline": roofline, "roofline_fr1desk": roof_fr1, "peak_source": peak_src,
             "cpu_baseline": cpu, "synthetic": synth,
         }

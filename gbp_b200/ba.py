@@ -567,6 +567,13 @@ class BAFactorGraph:
         if self._eager:
             self._enqueue_snapshot()
 
+    def reset_iters_since_relin(self, value=1):
+        """The client loop of ba.py:91-93 (`for factor in graph.factors: factor.iters_since_relin = 1`) as one call
+        (engine extension; assigning through the factor proxies does the same with one device fill)."""
+        self._flush()
+        self._eng.fill_iters(int(value))
+        self._invalidate((L.F_ITERS,))
+
     def robustify_all_factors(self):
         """gbp/gbp.py:82-84"""
         self._sweep(L.ST_ROBUSTIFY)
