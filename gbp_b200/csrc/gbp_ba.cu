@@ -91,6 +91,8 @@ struct gbp_ba_graph {
     long long n_slots = 0;
     bool robust = false;
     bool priors_set = false;
+    int cam_w = CAM_M;   // doubles per stored factor->keyframe message: 27, or 18 with the factored layout (kernel_variant 5)
+    bool pdl = false;    // programmatic dependent launch between the kernels of captured iterations (GBP_PDL=1, small graphs)
     long long launches = 0;
 
     // host copies (factor order)
@@ -128,6 +130,23 @@ struct gbp_ba_graph {
 
 namespace {
 
+// kernel launch with the programmatic-stream-serialisation attribute (the kernel may start while its predecessor in the
+// stream is still running and synchronises with griddepcontrol.wait, see pdl_wait() in gbp_kernels.cuh)
+template <typename P>
+cudaError_t launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, cudaStream_t stream, const P& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     SweepParams p{};
     p.tiles = g->tiles.p; p.lmk_idx = g->lmk_idx.p; p.z = g->z.p; p.linpoint = g->linpoint.p;
@@ -142,10 +161,30 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
 }
 
 template <int T>
-int launch_sweep_t(gbp_ba_graph* g, int stages) {
+int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
     const SweepParams p = sweep_params(g, stages);
     constexpr size_t smem = sweep_smem_bytes<T>();
     static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
+    if (pdl && g->cfg.kernel_variant == 0 && T <= 64) {   // inside captured iterations of small graphs only
+        constexpr int TP = T <= 64 ? T : 64;
+        cudaError_t e = g->robust ? launch_pdl(sweep_kernel<TP, true, true, 0, true>, g->n_tiles, TP, smem, g->stream, p)
+                                  : launch_pdl(sweep_kernel<TP, false, true, 0, true>, g->n_tiles, TP, smem, g->stream, p);
+        g->launches++;
+        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "sweep_kernel (programmatic launch): %s", cudaGetErrorString(e));
+        return GBP_OK;
+    }
+    if (g->cfg.kernel_variant == 5) {   // factored keyframe messages (18-double rows); T <= 64 checked at creation
+        constexpr int TP = T <= 64 ? T : 64;
+        constexpr size_t fsmem = sweep_smem_bytes<TP, true>();
+        static_assert(fsmem <= 48 * 1024, "factored sweep tile must fit the default dynamic shared memory limit");
+        if (g->robust)
+            sweep_kernel<TP, true, true, 0, false, true><<<g->n_tiles, TP, fsmem, g->stream>>>(p);
+        else
+            sweep_kernel<TP, false, true, 0, false, true><<<g->n_tiles, TP, fsmem, g->stream>>>(p);
+        g->launches++;
+        CU(cudaGetLastError());
+        return GBP_OK;
+    }
     if (g->cfg.kernel_variant == 4 && T <= 64) {   // persistent double-buffered kernel
         constexpr size_t psmem = sweep_persistent_smem_bytes<(T <= 64 ? T : 64)>();
         static_assert(psmem <= 48 * 1024, "persistent sweep stages must fit the default dynamic shared memory limit");
@@ -183,18 +222,19 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
     return GBP_OK;
 }
 
-int launch_sweep(gbp_ba_graph* g, int stages) {
+int launch_sweep(gbp_ba_graph* g, int stages, bool pdl = false) {
     if (g->n_tiles == 0) return GBP_OK;
     switch (g->T) {
-        case 32: return launch_sweep_t<32>(g, stages);
-        case 64: return launch_sweep_t<64>(g, stages);
-        default: return launch_sweep_t<128>(g, stages);
+        case 32: return launch_sweep_t<32>(g, stages, pdl);
+        case 64: return launch_sweep_t<64>(g, stages, pdl);
+        default: return launch_sweep_t<128>(g, stages, false);
     }
 }
 
 // landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise); parts: bit0 keyframes, bit1 landmarks
-int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
+int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, bool pdl = false) {
     BeliefParams p{};
+    p.pdl = pdl ? 1 : 0;
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
@@ -206,6 +246,19 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     const int per_cta = 128 / lanes;
     const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
+    if (pdl) {
+        cudaError_t e;
+        switch (lanes) {
+            case 1: e = launch_pdl(belief_kernel<1>, blocks, 128, 0, g->stream, p); break;
+            case 2: e = launch_pdl(belief_kernel<2>, blocks, 128, 0, g->stream, p); break;
+            case 4: e = launch_pdl(belief_kernel<4>, blocks, 128, 0, g->stream, p); break;
+            case 32: e = launch_pdl(belief_kernel<32>, blocks, 128, 0, g->stream, p); break;
+            default: e = launch_pdl(belief_kernel<8>, blocks, 128, 0, g->stream, p); break;
+        }
+        g->launches++;
+        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "belief_kernel (programmatic launch): %s", cudaGetErrorString(e));
+        return GBP_OK;
+    }
     switch (lanes) {
         case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
         case 2: belief_kernel<2><<<blocks, 128, 0, g->stream>>>(p); break;
@@ -309,9 +362,12 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     const long long before = g->launches;
     int rc = GBP_OK;
+    // inside the capture the kernel sequence is exactly [sweep, beliefs] x reps, which is what the early-start
+    // (programmatic) dependencies of the two kernels are written for; the first node depends on the stream normally
+    const bool pdl = g->pdl && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
     for (int r = 0; r < reps && rc == GBP_OK; ++r) {
-        rc = launch_sweep(g, stages);
-        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1);
+        rc = launch_sweep(g, stages, pdl);
+        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1, 3, pdl);
     }
     g->launches = before;  // capture does not execute
     cudaError_t e = cudaStreamEndCapture(g->stream, &graph);
@@ -387,6 +443,10 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     int T = cfg->tile_edges;
     if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
     if (T != 32 && T != 64 && T != 128) { delete g; return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
+    if (cfg->kernel_variant == 5) {
+        if (T == 128) { delete g; return fail(GBP_ERR_INVALID, "kernel_variant 5 (factored keyframe messages) needs tile_edges 32 or 64"); }
+        g->cam_w = CAM_MF;
+    }
     g->T = T;
     long long lblock = cfg->lmk_block;
     if (lblock <= 0) lblock = ((long long)L * LMK_B * 8 <= (24LL << 20)) ? std::max(L, 1) : 262144;
@@ -433,6 +493,10 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     }
     g->n_tiles = (int)tiles.size();
     g->n_slots = (long long)tiles.size() * T;
+    {   // experiment switch (round 2 decides the default): early-start dependencies between the kernels of an iteration
+        const char* v = getenv("GBP_PDL");
+        g->pdl = v && atoi(v) != 0 && g->n_tiles <= 8192 && cfg->kernel_variant == 0;
+    }
     if (g->n_slots >= (1LL << 31)) { delete g; return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
     g->h_slot_of_factor.assign((size_t)F, 0);
     {
@@ -486,7 +550,7 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
         ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
         ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
-        ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * CAM_M); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
+        ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
         ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
         ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3);
         ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
@@ -794,7 +858,10 @@ int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes) {
     DevBuf<uint32_t> tmp;
     CU(tmp.alloc((size_t)rows * fi.words));
     const long long n = rows * fi.words;
-    if (field == GBP_F_JACOBIAN_B) {
+    if (field == GBP_F_MSG_CAM && h->cam_w == CAM_MF) {
+        export_msg_cam_factored_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(reinterpret_cast<double*>(tmp.p), h->msg_cam.p,
+                                                                                         h->slot_of_factor.p, rows);
+    } else if (field == GBP_F_JACOBIAN_B) {
         export_jb_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->slot_of_factor.p, rows, h->linpoint.p, h->z.p, h->K,
                                                                             reinterpret_cast<double*>(tmp.p));
     } else {
@@ -833,8 +900,12 @@ int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes) {
     const long long n = rows * fi.words;
     cudaError_t e = cudaMemcpyAsync(tmp.p, host_src, need, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-        scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<uint32_t*>(field_dev_ptr(h, field)), tmp.p,
-                                                                            h->slot_of_factor.p, rows, fi.words);
+        if (field == GBP_F_MSG_CAM && h->cam_w == CAM_MF)
+            import_msg_cam_factored_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->msg_cam.p, reinterpret_cast<const double*>(tmp.p),
+                                                                                             h->slot_of_factor.p, rows);
+        else
+            scatter_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<uint32_t*>(field_dev_ptr(h, field)), tmp.p,
+                                                                                h->slot_of_factor.p, rows, fi.words);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

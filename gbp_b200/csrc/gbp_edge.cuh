@@ -14,6 +14,7 @@
 namespace gbp {
 
 constexpr int CAM_B = 33, LMK_B = 12, CAM_M = 27, LMK_M = 9;
+constexpr int CAM_MF = 18;   // keyframe message with factored precision: eta[6] | W[2][6], Lambda = W^T W (kernel_variant 5)
 
 enum : int { ST_ROBUSTIFY = 1, ST_RELIN = 2, ST_MESSAGES = 4, ST_BELIEFS = 8, ST_LOCAL_DAMPING = 16 };
 
@@ -52,9 +53,11 @@ struct EdgeRegs {
 // robustify -> relinearise -> messages for ONE edge.  my_* are the edge's rows in shared memory
 // (read, then overwritten in place with the new messages / linearisation point); s_cb is the
 // keyframe belief row shared by the whole tile.  Returns true when the edge relinearised.
-template <bool ROBUST>
+// FACTORED: my_mc is an 18-double row eta[6] | W[2][6] (Lambda = W^T W) and my_full receives the message in the full
+// 27-double form eta | Lambda for the keyframe-side sum (whenever the stages include the belief sums).
+template <bool ROBUST, bool FACTORED = false>
 GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const double* s_cb, double* my_lp, double* my_mc,
-                       double* my_ml) {
+                       double* my_ml, double* my_full = nullptr) {
     const double* z = r.z;
     const double* bl = r.bl;
     int it = r.it, fl = r.fl;
@@ -136,8 +139,15 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
             double P[21], ev[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) ev[k] = s_cb[k] - my_mc[k];
+            if (FACTORED) {
+                double old_lam[21];
+                expand_factored6(my_mc + 6, old_lam);
 #pragma unroll
-            for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
+                for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - old_lam[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
+            }
             message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
         }
         // message to the keyframe: marginalise the landmark (3x3 Cholesky); written in place
@@ -147,12 +157,18 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
             for (int k = 0; k < 3; ++k) ev[k] = bl[k] - my_ml[k];
 #pragma unroll
             for (int k = 0; k < 6; ++k) P[k] = bl[3 + k] - my_ml[3 + k];
-            message<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
+            if (FACTORED) message_factored<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
+            else message<6, 3>(J, J + 6, b, var, P, ev, damping, my_mc, my_mc, my_mc + 6);
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) my_ml[k] = nl_eta[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) my_ml[3 + k] = nl_lam[k];
+    }
+    if (FACTORED && (p.stages & ST_BELIEFS)) {   // full form of the (new or stored) message for the keyframe-side sum
+#pragma unroll
+        for (int k = 0; k < 6; ++k) my_full[k] = my_mc[k];
+        expand_factored6(my_mc + 6, my_full + 6);
     }
     p.iters[e] = it;
     p.flags[e] = fl;

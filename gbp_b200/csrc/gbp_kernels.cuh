@@ -3,6 +3,7 @@
 // Data layout in HBM (all float64 unless noted; "slot" = position of an edge in the
 // engine's storage order, tile t owns slots [t*T, t*T + count)):
 //   msg_cam   [slots][27]  factor->keyframe message  eta[6] | Lambda packed[21]
+//             [slots][18]  ... or with the rank-2 precision factored: eta[6] | W[2][6], Lambda = W^T W (kernel_variant 5)
 //   msg_lmk   [slots][9]   factor->landmark message  eta[3] | Lambda packed[6]
 //   linpoint  [slots][9]   linearisation point [t, w, y]
 //   z         [slots][2]   measurement
@@ -96,8 +97,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool HINTS>
-__device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e, EdgeRegs& r) {
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; everything it reads from that predecessor must come after
+// pdl_wait() (returns once the predecessor grid has completed and its writes are visible; no-op for a normal launch).
+// pdl_launch_dependents() lets the NEXT kernel of the stream start early in the same way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// scalars of the edge (none of them is written by belief_kernel); returns the landmark index for the gather
+__device__ __forceinline__ int load_edge_scalars(const SweepParams& p, long long e, EdgeRegs& r) {
     const int lmk = p.lmk_idx[e];
     r.it = p.iters[e];
     r.fl = p.flags[e];
@@ -105,6 +113,12 @@ __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e
     const double2 zz = reinterpret_cast<const double2*>(p.z)[e];
     r.z[0] = zz.x;
     r.z[1] = zz.y;
+    return lmk;
+}
+
+// the dependent gather: 96 B landmark belief row (six 16 B loads)
+template <bool HINTS>
+__device__ __forceinline__ void gather_lmk_belief(const SweepParams& p, int lmk, EdgeRegs& r) {
     const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
     uint64_t pol = 0;
     if (HINTS) pol = policy_evict_last();
@@ -114,6 +128,12 @@ __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e
         r.bl[2 * k] = v.x;
         r.bl[2 * k + 1] = v.y;
     }
+}
+
+template <bool HINTS>
+__device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e, EdgeRegs& r) {
+    const int lmk = load_edge_scalars(p, e, r);
+    gather_lmk_belief<HINTS>(p, lmk, r);
 }
 
 // column sums of the tile's (new) messages to its keyframe -> tile_partial[tile][27]
@@ -150,15 +170,23 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
 // ----------------------------------------------------------------------------------------
 // Compiled for 384 resident threads per SM (<= 170 registers, no spills).  OCC = 1: 512 threads per SM (128 registers,
 // a few spilled doubles) -- measured SLOWER (1.32 vs 1.25 ms on the 10 M-factor graph), kept as kernel_variant 3 for A/B.
-template <int T, bool ROBUST, bool HINTS, int OCC = 0>
+// PDL = true (small, latency-bound graphs; launched with the programmatic-serialisation attribute): the prologue -- barrier
+// init, bulk loads of the tile's rows, the edge's scalars -- runs while belief_kernel of the previous iteration is still
+// finishing; only the belief rows are read after pdl_wait().  Everything read before the wait was written by the sweep of
+// the previous iteration, which had completed before that belief_kernel released its dependents.
+// FACT = true (kernel_variant 5): the keyframe messages live in HBM with their rank-2 precision factored (18 doubles per
+// row instead of 27: 144 B less traffic per edge and sweep); the threads expand them into s_full for the keyframe-side sum.
+template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false>
 __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
-    double* s_mc = smem;                 // [T][27]
-    double* s_ml = s_mc + T * CAM_M;     // [T][9]
+    constexpr int CW = FACT ? CAM_MF : CAM_M;
+    double* s_mc = smem;                 // [T][27]  (or [T][18] factored)
+    double* s_ml = s_mc + T * CW;        // [T][9]
     double* s_lp = s_ml + T * LMK_M;     // [T][9]
     double* s_cb = s_lp + T * 9;         // [33] keyframe belief (+pad to 34)
     double* s_red = s_cb + 34;           // [T/32][27]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);
+    double* s_full = s_red + (T / 32) * CAM_M + 2;   // [T][27] full-form messages of the tile (FACT only)
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
@@ -169,27 +197,38 @@ __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
+    if (PDL) pdl_launch_dependents();   // belief_kernel behind us may be scheduled; it waits for this grid before it reads
     if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)n_even * (CAM_M + LMK_M + 9) * 8);
+        mbar_expect_tx(bar, (uint32_t)n_even * (CW + LMK_M + 9) * 8);
         if (HINTS) {
             const uint64_t pol = policy_evict_first();
-            bulk_g2s_hint(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar, pol);
+            bulk_g2s_hint(s_mc, p.msg_cam + base * CW, (uint32_t)n_even * CW * 8, bar, pol);
             bulk_g2s_hint(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar, pol);
             bulk_g2s_hint(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar, pol);
         } else {
-            bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
+            bulk_g2s(s_mc, p.msg_cam + base * CW, (uint32_t)n_even * CW * 8, bar);
             bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
             bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
         }
     }
-    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
     EdgeRegs r;
-    if (tid < n) load_edge_regs<HINTS>(p, base + tid, r);
+    if (PDL) {
+        int lmk = 0;
+        if (tid < n) lmk = load_edge_scalars(p, base + tid, r);
+        pdl_wait();           // beliefs of the previous iteration are complete and visible from here on
+        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
+        if (tid < n) gather_lmk_belief<HINTS>(p, lmk, r);
+    } else {
+        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
+        if (tid < n) load_edge_regs<HINTS>(p, base + tid, r);
+    }
     __syncthreads();          // s_cb visible
     mbar_wait(bar, 0);        // bulk loads landed
 
     bool relin = false;
-    if (tid < n) relin = edge_sweep<ROBUST>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
+    if (tid < n)
+        relin = edge_sweep<ROBUST, FACT>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
+                                         FACT ? s_full + tid * CAM_M : nullptr);
     fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
@@ -199,20 +238,20 @@ __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const
             // and the linearisation points are marked evict_first
             const uint64_t pol = policy_evict_first();
             if (p.stages & ST_MESSAGES) {
-                bulk_s2g_hint(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8, pol);
+                bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
                 bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
             }
             if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
         } else {
             if (p.stages & ST_MESSAGES) {
-                bulk_s2g(p.msg_cam + base * CAM_M, s_mc, (uint32_t)n_even * CAM_M * 8);
+                bulk_s2g(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8);
                 bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
             }
             if (any_relin) bulk_s2g(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72);
         }
         bulk_commit();
     }
-    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
+    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, FACT ? s_full : s_mc, s_red);
     if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
 }
 
@@ -344,9 +383,9 @@ __global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
     if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
 }
 
-template <int T>
+template <int T, bool FACT = false>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(double) * (size_t)(T * (CAM_M + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
+    return sizeof(double) * (size_t)(T * ((FACT ? CAM_MF + CAM_M : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -373,6 +412,7 @@ struct BeliefParams {
     double* lmk_mu;          // [L][3]
     int L, C, finalise;
     int parts;               // bit0: keyframe CTAs, bit1: landmark CTAs (multi-GPU runs them as two launches)
+    int pdl;                 // launched with programmatic serialisation behind sweep_kernel
 };
 
 __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out) {
@@ -412,6 +452,10 @@ __device__ __forceinline__ void load_row9(const double* __restrict__ row, bool e
 template <int LMK_LANES>
 __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     constexpr int LMK_PER_CTA = 128 / LMK_LANES;
+    if (p.pdl) {
+        pdl_wait();                 // every message / tile partial of this iteration's sweep is complete and visible
+        pdl_launch_dependents();    // only now: the next sweep's prologue reads rows that sweep wrote
+    }
     const int cam_blocks = (p.parts & 1) ? (p.C + 3) / 4 : 0;
     if ((int)blockIdx.x < cam_blocks) {
         // ---- keyframes first in the grid: their serial tile loops overlap the landmark CTAs
@@ -745,6 +789,29 @@ __global__ void scatter_rows_kernel(uint32_t* __restrict__ dst, const uint32_t* 
     const long long f = i / W;
     const int w = (int)(i - f * W);
     dst[(long long)slot_of_factor[f] * W + w] = src[i];
+}
+// GBP_F_MSG_CAM with the factored layout: the client always sees eta[6] | Lambda[21] in factor order
+__global__ void export_msg_cam_factored_kernel(double* __restrict__ dst, const double* __restrict__ src,
+                                               const int* __restrict__ slot_of_factor, long long F) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double* row = src + (long long)slot_of_factor[f] * CAM_MF;
+    double W[12], lam[21];
+    for (int k = 0; k < 12; ++k) W[k] = row[6 + k];
+    expand_factored6(W, lam);
+    for (int k = 0; k < 6; ++k) dst[f * CAM_M + k] = row[k];
+    for (int k = 0; k < 21; ++k) dst[f * CAM_M + 6 + k] = lam[k];
+}
+__global__ void import_msg_cam_factored_kernel(double* __restrict__ dst, const double* __restrict__ src,
+                                               const int* __restrict__ slot_of_factor, long long F) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double* row = dst + (long long)slot_of_factor[f] * CAM_MF;
+    double lam[21], W[12];
+    for (int k = 0; k < 21; ++k) lam[k] = src[f * CAM_M + 6 + k];
+    factor_rank2_6(lam, W);
+    for (int k = 0; k < 6; ++k) row[k] = src[f * CAM_M + k];
+    for (int k = 0; k < 12; ++k) row[6 + k] = W[k];
 }
 __global__ void fill_iters_kernel(int* iters, long long n_slots, int value) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

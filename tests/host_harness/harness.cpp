@@ -67,8 +67,9 @@ struct HostSweep {
     long F = 0;
     SweepParams prm{};
     bool robust = false;
+    bool factored = false;   // keyframe messages stored as eta[6] | W[2][6] (kernel_variant 5); msg_full = their 27-wide form
     std::vector<int> cam, lmk, iters, flags;
-    std::vector<double> z, linpoint, msg_cam, msg_lmk, sigma2a, cam_belief, lmk_belief, cam_prior, lmk_prior;
+    std::vector<double> z, linpoint, msg_cam, msg_lmk, sigma2a, cam_belief, lmk_belief, cam_prior, lmk_prior, msg_full;
 
     void sweep(int stages) {
         SweepParams p = prm;
@@ -84,16 +85,25 @@ struct HostSweep {
             const double* cb = &cam_belief[(size_t)cam[e] * CAM_B];
             // beliefs are only read during a sweep, so updating the edge's rows in place is the kernel's
             // "stage in shared memory, overwrite, store back"
-            if (robust) edge_sweep<true>(p, e, r, cb, &linpoint[9 * e], &msg_cam[(size_t)CAM_M * e], &msg_lmk[(size_t)LMK_M * e]);
-            else edge_sweep<false>(p, e, r, cb, &linpoint[9 * e], &msg_cam[(size_t)CAM_M * e], &msg_lmk[(size_t)LMK_M * e]);
+            double *lp = &linpoint[9 * e], *ml = &msg_lmk[(size_t)LMK_M * e];
+            if (factored) {
+                double *mc = &msg_cam[(size_t)CAM_MF * e], *full = &msg_full[(size_t)CAM_M * e];
+                if (robust) edge_sweep<true, true>(p, e, r, cb, lp, mc, ml, full);
+                else edge_sweep<false, true>(p, e, r, cb, lp, mc, ml, full);
+            } else {
+                double* mc = &msg_cam[(size_t)CAM_M * e];
+                if (robust) edge_sweep<true>(p, e, r, cb, lp, mc, ml);
+                else edge_sweep<false>(p, e, r, cb, lp, mc, ml);
+            }
         }
     }
 
     // VariableNode.update_belief (gbp/gbp.py:176-198): messages summed in factor order, then the prior
     void beliefs() {
         std::vector<double> ca((size_t)C * CAM_M, 0.0), la((size_t)L * LMK_M, 0.0);
+        const std::vector<double>& mc = factored ? msg_full : msg_cam;   // the kernel sums the tile's 27-wide rows
         for (long e = 0; e < F; ++e) {
-            for (int k = 0; k < CAM_M; ++k) ca[(size_t)cam[e] * CAM_M + k] += msg_cam[(size_t)CAM_M * e + k];
+            for (int k = 0; k < CAM_M; ++k) ca[(size_t)cam[e] * CAM_M + k] += mc[(size_t)CAM_M * e + k];
             for (int k = 0; k < LMK_M; ++k) la[(size_t)lmk[e] * LMK_M + k] += msg_lmk[(size_t)LMK_M * e + k];
         }
         for (int c = 0; c < C; ++c) {
@@ -185,7 +195,28 @@ void hs_scale_priors(void* hv, double f) {
     for (double& v : h->lmk_prior) v *= f;
 }
 
-void hs_update_beliefs(void* hv) { static_cast<HostSweep*>(hv)->beliefs(); }
+// gbp_ba_update_beliefs: a sweep that only forms the keyframe-side sums of the STORED messages, then the beliefs
+void hs_update_beliefs(void* hv) {
+    HostSweep* h = static_cast<HostSweep*>(hv);
+    h->sweep(ST_BELIEFS);
+    h->beliefs();
+}
+
+// switch to the factored keyframe-message layout (before the first sweep: messages are still zero)
+void hs_set_factored(void* hv, int on) {
+    HostSweep* h = static_cast<HostSweep*>(hv);
+    h->factored = on != 0;
+    h->msg_cam.assign((size_t)h->F * (h->factored ? CAM_MF : CAM_M), 0.0);
+    h->msg_full.assign(h->factored ? (size_t)h->F * CAM_M : 0, 0.0);
+}
+
+// round trip of a client-written keyframe message through the factored layout (gbp_ba_write / gbp_ba_read)
+void hh_factor_roundtrip(const double* lam21, long n, double* W12, double* lam21_out) {
+    for (long i = 0; i < n; ++i) {
+        factor_rank2_6(lam21 + 21 * i, W12 + 12 * i);
+        expand_factored6(W12 + 12 * i, lam21_out + 21 * i);
+    }
+}
 
 void hs_iterate(void* hv, int n, int robustify, int local_relin) {
     HostSweep* h = static_cast<HostSweep*>(hv);
@@ -229,7 +260,16 @@ void hs_read(void* hv, int field, double* out) {
         case 1: v = &h->lmk_belief; break;
         case 2: v = &h->cam_prior; break;
         case 3: v = &h->lmk_prior; break;
-        case 4: v = &h->msg_cam; break;
+        case 4:
+            if (h->factored) {   // what gbp_ba_read returns: the full 27-wide form
+                for (long e = 0; e < h->F; ++e) {
+                    for (int k = 0; k < 6; ++k) out[(size_t)CAM_M * e + k] = h->msg_cam[(size_t)CAM_MF * e + k];
+                    expand_factored6(&h->msg_cam[(size_t)CAM_MF * e + 6], out + (size_t)CAM_M * e + 6);
+                }
+                return;
+            }
+            v = &h->msg_cam;
+            break;
         case 5: v = &h->msg_lmk; break;
         case 6: v = &h->linpoint; break;
         case 9: v = &h->sigma2a; break;

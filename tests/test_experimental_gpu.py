@@ -1,0 +1,99 @@
+"""GPU checks of engine variants that are built and CPU-verified (tests/test_math_host.py runs their arithmetic through
+the reference fixtures) but have not had their hardware run yet: the factored keyframe-message layout (kernel_variant 5)
+and programmatic dependent launches between the kernels of an iteration (GBP_PDL=1).  They run when
+GBP_TEST_EXPERIMENTAL=1 is set; the default `-m gpu` suite covers the default engine only."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_configs, golden_problem, load_golden, relerr
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("GBP_TEST_EXPERIMENTAL", "0") in ("", "0"),
+                                 reason="experimental engine variants: set GBP_TEST_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_float"])
+def test_factored_messages_against_reference_fixture(name):
+    """kernel_variant 5 through every checkpoint of the reference run (messages are read back in full form)."""
+    from gbp_b200.ba import create_ba_graph
+    from test_ba_gpu import TOL_CONVERGED, TOL_EARLY, _check_snapshot, _run_loop
+    G = load_golden(name)
+    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=5)
+    cks = set(G["checkpoints"].tolist())
+    float_impl = bool(G["float_impl"])
+
+    def on_iter(i):
+        if i in cks:
+            _check_snapshot(graph, G, f"s{i}", TOL_EARLY if i <= 2 else (TOL_CONVERGED if float_impl else 1e-5))
+
+    are, en, nrel = _run_loop(graph, G, int(G["n_iters"]), on_iter)
+    assert np.array_equal(nrel, G["n_relin"])
+    tol = 1e-3 if float_impl else 1e-6       # see tests/test_math_host.py on the float-implementation trace
+    assert relerr(are, G["are"]) < tol and relerr(en, G["energy"]) < tol
+    graph.close()
+
+
+def test_factored_messages_fr1desk_200_iterations():
+    from gbp_b200.ba import create_ba_graph
+    from test_ba_gpu import TOL_CONVERGED, _check_snapshot, _run_loop
+    G = load_golden("fr1desk")
+    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=5)
+    are, en, nrel = _run_loop(graph, G, 200)
+    _check_snapshot(graph, G, "s199", TOL_CONVERGED)
+    assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
+    assert np.max(np.abs(nrel - G["n_relin"])) <= 2
+    graph.close()
+
+
+def test_factored_messages_equal_full_layout_and_round_trip():
+    """Same graph, both layouts, 64-edge tiles with landmark blocks: same state; a message table written by the client
+    (full form) reads back unchanged and the sweep continues identically from it."""
+    from gbp_b200 import _lib as L
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200.synthetic import make_synthetic
+    prob = make_synthetic(20, 2000, 10, seed=0)
+    cfg = dict(gauss_noise_std=2, loss="huber", Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
+    a = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512, kernel_variant=0)
+    b = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512, kernel_variant=5)
+    for g in (a, b):
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+        g.iterate(12, robustify=True, local_relin=True)
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ADAPTIVE_VAR):
+        assert relerr(b._eng.read(f), a._eng.read(f)) < 1e-9, f
+    assert np.array_equal(a._eng.read(L.F_ITERS), b._eng.read(L.F_ITERS))
+    m = a._eng.read(L.F_MSG_CAM).copy()
+    b._eng.write(L.F_MSG_CAM, m)
+    back = b._eng.read(L.F_MSG_CAM)
+    scale = np.maximum(np.abs(m).max(axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(back - m) / scale) < 1e-11
+    for g in (a, b):
+        g.update_all_beliefs()
+        g.iterate(3, robustify=True, local_relin=True)
+    assert relerr(b.get_means(), a.get_means()) < 1e-9
+    a.close(); b.close()
+
+
+def test_programmatic_launches_do_not_change_results(monkeypatch):
+    """GBP_PDL=1: the kernels of captured iterations start early and synchronise on the device; bit-identical state."""
+    from gbp_b200 import _lib as L
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden("fr1desk")
+    graphs = []
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("GBP_PDL", pdl)
+        g = create_ba_graph(golden_problem(G), golden_configs(G))
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+        g.iterate(3, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
+        g.iterate(5, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
+        g.iterate(192, robustify=True, local_relin=True)
+        graphs.append(g)
+    a, b = graphs
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ITERS, L.F_FLAGS):
+        assert np.array_equal(a._eng.read(f), b._eng.read(f)), f
+    mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
+    assert relerr(b.get_means(), mu_ref) < 1e-4
+    a.close(); b.close()

@@ -45,6 +45,8 @@ def hh():
     lib.hs_fill_iters.argtypes = [vp, C.c_int]
     lib.hs_metrics.argtypes = [vp, vp]
     lib.hs_read.argtypes = lib.hs_read_int.argtypes = [vp, C.c_int, vp]
+    lib.hs_set_factored.argtypes = [vp, C.c_int]
+    lib.hh_factor_roundtrip.argtypes = [vp, C.c_long, vp, vp]
     return lib
 
 
@@ -63,7 +65,7 @@ def _sym(packed, n):
 class HostSweep:
     """ba.py-shaped driver of the harness' whole-graph loops (factor order = camera-major like the reference)."""
 
-    def __init__(self, lib, G, cfg):
+    def __init__(self, lib, G, cfg, factored=False):
         self.lib = lib
         cam_id = np.asarray(G["in_cam_id"], dtype=np.int64)
         order = np.argsort(cam_id, kind="stable")
@@ -78,6 +80,8 @@ class HostSweep:
         self.h = lib.hs_create(float(cfg["gauss_noise_std"]), self.eta_damping, float(cfg["beta"]), float(cfg.get("Nstds", 3.0)),
                                int(cfg["num_undamped_iters"]), int(cfg["min_linear_iters"]), LOSS[cfg.get("loss")],
                                self.C, self.L, self.F, _p(self.cam), _p(self.lmk), _p(z), _p(cam0), _p(lmk0), _p(k4))
+        if factored:
+            lib.hs_set_factored(self.h, 1)
 
     def close(self):
         self.lib.hs_destroy(self.h)
@@ -208,6 +212,22 @@ def test_robust_variance(hh, loss):
             assert flag.value == 0 and v == var0
 
 
+def test_factored_message_round_trip(hh):
+    """A keyframe message written by a client in full form survives the factored layout: rank-2 PSD matrices exactly
+    (to rounding), the zero message, rank 1; W^T W of a random W is reproduced although W itself is not unique."""
+    rng = np.random.default_rng(5)
+    W = rng.normal(size=(300, 2, 6)) * rng.uniform(0.1, 300, size=(300, 1, 1))
+    W[0] = 0.0
+    W[1, 1] = 0.0
+    lam = np.einsum("nki,nkj->nij", W, W)
+    packed = np.ascontiguousarray(lam[:, _IU6[0], _IU6[1]])
+    Wout, back = np.empty((300, 12)), np.empty((300, 21))
+    hh.hh_factor_roundtrip(_p(packed), 300, _p(Wout), _p(back))
+    scale = np.maximum(np.abs(packed).max(axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(back - packed) / scale) < 1e-12
+    assert np.all(Wout[0] == 0.0) and np.all(np.isfinite(Wout))
+
+
 # ---------------------------------------------------------------------------------------------- whole trajectories
 def _check_state(s, G, key, tol):
     fs = G["fsample"]
@@ -227,13 +247,15 @@ def _check_state(s, G, key, tol):
     assert not bad, (key, bad)
 
 
+@pytest.mark.parametrize("factored", [False, True], ids=["full", "factored"])
 @pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float"])
-def test_edge_sweep_trajectory_against_reference_fixture(hh, name):
+def test_edge_sweep_trajectory_against_reference_fixture(hh, name, factored):
     """Every checkpoint of the reference run (all loss modes, --float_implementation): beliefs, sampled messages and
-    linearisation points, every factor's iters_since_relin and damping flag, the ARE / energy / relinearisation traces."""
+    linearisation points, every factor's iters_since_relin and damping flag, the ARE / energy / relinearisation traces.
+    `factored` = the compressed keyframe-message layout (eta | W with Lambda = W^T W, kernel_variant 5)."""
     G = load_golden(name)
     cfg = golden_configs(G)
-    s = HostSweep(hh, G, cfg)
+    s = HostSweep(hh, G, cfg, factored)
     cks = set(G["checkpoints"].tolist())
     float_impl = bool(G["float_impl"])
 
@@ -254,12 +276,13 @@ def test_edge_sweep_trajectory_against_reference_fixture(hh, name):
     s.close()
 
 
-def test_edge_sweep_fr1desk_200_iterations(hh):
+@pytest.mark.parametrize("factored", [False, True], ids=["full", "factored"])
+def test_edge_sweep_fr1desk_200_iterations(hh, factored):
     """BASELINE config 3 on the host build of the device arithmetic: converged means AND precisions within the
     north-star tolerance (1e-4 relative) of the reference, identical relinearisation counts at all 201 reads."""
     G = load_golden("fr1desk")
     cfg = golden_configs(G)
-    s = HostSweep(hh, G, cfg)
+    s = HostSweep(hh, G, cfg, factored)
     are, en, nrel = s.run(200, cfg["prior_std_weaker_factor"])
     assert np.array_equal(nrel, G["n_relin"])
     assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
