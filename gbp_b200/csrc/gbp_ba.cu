@@ -173,14 +173,26 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
         if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "sweep_kernel (programmatic launch): %s", cudaGetErrorString(e));
         return GBP_OK;
     }
-    if (g->cfg.kernel_variant == 5) {   // factored keyframe messages (18-double rows); T <= 64 checked at creation
+    if (g->cfg.kernel_variant >= 5 && g->cfg.kernel_variant <= 9) {
+        // 5 factored keyframe messages (18-double rows; T <= 64 checked at creation); 6 full rows + early issue;
+        // 7 factored + early issue; 8 / 9 = 7 / 6 compiled for 7 CTAs of 64 threads per SM (146 registers)
         constexpr int TP = T <= 64 ? T : 64;
         constexpr size_t fsmem = sweep_smem_bytes<TP, true>();
+        constexpr size_t esmem = sweep_smem_bytes<TP, false>();
         static_assert(fsmem <= 48 * 1024, "factored sweep tile must fit the default dynamic shared memory limit");
-        if (g->robust)
-            sweep_kernel<TP, true, true, 0, false, true><<<g->n_tiles, TP, fsmem, g->stream>>>(p);
-        else
-            sweep_kernel<TP, false, true, 0, false, true><<<g->n_tiles, TP, fsmem, g->stream>>>(p);
+#define GBP_LAUNCH_V(OCC, FACT, EARLY, SMEM)                                                                        \
+        do {                                                                                                        \
+            if (g->robust) sweep_kernel<TP, true, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);  \
+            else sweep_kernel<TP, false, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);           \
+        } while (0)
+        switch (g->cfg.kernel_variant) {
+            case 5: GBP_LAUNCH_V(0, true, false, fsmem); break;
+            case 6: GBP_LAUNCH_V(0, false, true, esmem); break;
+            case 7: GBP_LAUNCH_V(0, true, true, fsmem); break;
+            case 8: GBP_LAUNCH_V(2, true, true, fsmem); break;
+            default: GBP_LAUNCH_V(2, false, true, esmem); break;
+        }
+#undef GBP_LAUNCH_V
         g->launches++;
         CU(cudaGetLastError());
         return GBP_OK;
@@ -443,9 +455,9 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     int T = cfg->tile_edges;
     if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
     if (T != 32 && T != 64 && T != 128) { delete g; return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
-    if (cfg->kernel_variant == 5) {
-        if (T == 128) { delete g; return fail(GBP_ERR_INVALID, "kernel_variant 5 (factored keyframe messages) needs tile_edges 32 or 64"); }
-        g->cam_w = CAM_MF;
+    if (cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) {
+        if (T == 128) { delete g; return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
+        if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8) g->cam_w = CAM_MF;
     }
     g->T = T;
     long long lblock = cfg->lmk_block;

@@ -176,8 +176,12 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
 // the previous iteration, which had completed before that belief_kernel released its dependents.
 // FACT = true (kernel_variant 5): the keyframe messages live in HBM with their rank-2 precision factored (18 doubles per
 // row instead of 27: 144 B less traffic per edge and sweep); the threads expand them into s_full for the keyframe-side sum.
-template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false>
-__global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const SweepParams p) {
+// EARLY = true (kernel_variants 6-9): nothing on the critical path waits for the tile descriptor.  A tile owns T slots
+// (padding slots hold landmark 0, zero rows, iters = -1), so the bulk loads fetch all T rows and every thread loads its
+// scalars and gathers its landmark row unconditionally at once; the descriptor (count, keyframe) arrives in parallel
+// and is only needed for the keyframe row and the stores.  Dependent DRAM round trips before the edge code: 3 -> 2.
+template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false, bool EARLY = false>
+__global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
     constexpr int CW = FACT ? CAM_MF : CAM_M;
     double* s_mc = smem;                 // [T][27]  (or [T][18] factored)
@@ -190,15 +194,30 @@ __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
+    const long long base = (long long)tile * T;
+    EdgeRegs r;
+    if (EARLY) {
+        if (tid == 0) {
+            mbar_init(bar, 1);          // only this thread touches the barrier before the __syncthreads below
+            mbar_expect_tx(bar, (uint32_t)T * (CW + LMK_M + 9) * 8);
+            const uint64_t pol = policy_evict_first();
+            bulk_g2s_hint(s_mc, p.msg_cam + base * CW, (uint32_t)T * CW * 8, bar, pol);
+            bulk_g2s_hint(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)T * LMK_M * 8, bar, pol);
+            bulk_g2s_hint(s_lp, p.linpoint + base * 9, (uint32_t)T * 72, bar, pol);
+        }
+        const int lmk = load_edge_scalars(p, base + tid, r);
+        gather_lmk_belief<HINTS>(p, lmk, r);
+    }
     const Tile tl = p.tiles[tile];
     const int n = tl.count;
     const int n_even = (n + 1) & ~1;     // bulk copies move multiples of 16 B; the extra row is tile padding
-    const long long base = (long long)tile * T;
 
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    if (!EARLY) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+    }
     if (PDL) pdl_launch_dependents();   // belief_kernel behind us may be scheduled; it waits for this grid before it reads
-    if (tid == 0) {
+    if (!EARLY && tid == 0) {
         mbar_expect_tx(bar, (uint32_t)n_even * (CW + LMK_M + 9) * 8);
         if (HINTS) {
             const uint64_t pol = policy_evict_first();
@@ -211,8 +230,9 @@ __global__ void __launch_bounds__(T, OCC ? 512 / T : 384 / T) sweep_kernel(const
             bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
         }
     }
-    EdgeRegs r;
-    if (PDL) {
+    if (EARLY) {
+        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
+    } else if (PDL) {
         int lmk = 0;
         if (tid < n) lmk = load_edge_scalars(p, base + tid, r);
         pdl_wait();           // beliefs of the previous iteration are complete and visible from here on

@@ -24,6 +24,7 @@ from gbp_b200.synthetic import make_synthetic  # noqa: E402
 
 CFG = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
 OUT = os.path.join(ROOT, "gpurun_out", "ab_variants.jsonl")
+VARIANTS, PDL = [5, 6, 7, 9], False
 
 
 def emit(d):
@@ -45,7 +46,10 @@ def fr1desk(reps):
     prob = balio.BALProblem(G["in_cam_id"], G["in_lmk_id"], G["in_z"], G["in_cam0"], G["in_lmk0"], G["in_K"])
     mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
     base = None
-    for name, env, variant in (("default", "0", 0), ("pdl", "1", 0), ("factored", "0", 5), ("default_again", "0", 0)):
+    runs = [("default", "0", 0)] + [(f"variant{v}", "0", v) for v in VARIANTS] + [("default_again", "0", 0)]
+    if PDL:
+        runs.insert(1, ("pdl", "1", 0))
+    for name, env, variant in runs:
         try:
             os.environ["GBP_PDL"] = env
             g = create_ba_graph(prob, CFG, kernel_variant=variant)
@@ -74,7 +78,7 @@ def fr1desk(reps):
 def synthetic(cams, lmks, iters):
     prob = make_synthetic(cams, lmks, 10, seed=0)
     base = None
-    for name, variant in (("default", 0), ("factored", 5)):
+    for name, variant in [("default", 0)] + [(f"variant{v}", v) for v in VARIANTS] + [("default_again", 0)]:
         try:
             g = create_ba_graph(prob, CFG, kernel_variant=variant)
             e = g._eng
@@ -83,7 +87,7 @@ def synthetic(cams, lmks, iters):
             tot, sw = e.time_iterations(iters, True, True, per_kernel=True)
             tot_g, _ = e.time_iterations(iters, True, True, per_kernel=False)
             F, L, C = e.F, e.L, e.C
-            per_edge = 684 if variant == 0 else 540          # bytes the sweep really moves per edge (ids 4, z 16, linpoint 72, iters/flags 16, messages)
+            per_edge = 540 if variant in (5, 7, 8) else 684          # bytes the sweep really moves per edge (ids 4, z 16, linpoint 72, iters/flags 16, messages)
             mu = g.get_means()
             if base is None:
                 base = mu
@@ -105,7 +109,11 @@ if __name__ == "__main__":
     ap.add_argument("--lmks", type=int, default=1_000_000)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--skip-synthetic", action="store_true")
+    ap.add_argument("--variants", default="5,6,7,9")
+    ap.add_argument("--pdl", action="store_true")
     a = ap.parse_args()
+    VARIANTS = [int(v) for v in a.variants.split(",") if v]
+    PDL = a.pdl
     fr1desk(a.reps)
     if not a.skip_synthetic:
         synthetic(a.cams, a.lmks, a.iters)
