@@ -224,6 +224,14 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
             sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
         else
             sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+    } else if (g->n_tiles > 8192 && T <= 64) {
+        // default for large (HBM-bound) graphs: early issue -- no load of the prologue waits for the tile descriptor
+        // (measured on the 10 M-factor graph: 1.186 -> 1.110 ms per launch, 6.34 TB/s of DRAM traffic)
+        constexpr int TP = T <= 64 ? T : 64;
+        if (g->robust)
+            sweep_kernel<TP, true, true, 0, false, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
+        else
+            sweep_kernel<TP, false, true, 0, false, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
     } else if (g->robust) {
         sweep_kernel<T, true, true><<<g->n_tiles, T, smem, g->stream>>>(p);
     } else {

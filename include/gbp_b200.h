@@ -55,11 +55,14 @@ typedef struct gbp_config {
     int32_t loss;                /* gbp_loss (gbp/gbp.py:243)                                  */
     int32_t tile_edges;          /* 0 = auto; else 32/64/128 edges per tile (engine tuning)    */
     int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
-    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default); 1 = first-version LDG kernel; 2 = TMA, no hints;
+    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default; graphs of more than 8192 tiles use its
+                                        early-issue build, = variant 6); 1 = first-version LDG kernel; 2 = TMA, no hints;
                                     3 = 128-register build; 4 = persistent double-buffered (tiles of 32 / 64);
                                     5 = factor->keyframe messages stored with their rank-2 precision factored (eta[6] | W[2][6],
                                         Lambda = W^T W: 144 B less traffic per edge and sweep; tiles of 32 / 64).  GBP_F_MSG_CAM
-                                        reads and writes keep the full eta[6] | Lambda[21] form. */
+                                        reads and writes keep the full eta[6] | Lambda[21] form;
+                                    6 = early issue: bulk loads, scalars and the landmark gather do not wait for the tile descriptor;
+                                    7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments) */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */
