@@ -65,10 +65,12 @@ def ncu_traffic(key):
         return None
 
 
-def b_alg(F, L, C):
-    """Algorithmic bytes of one synchronous iteration and of the sweep kernel alone."""
-    total = 696 * F + 264 * L + 744 * C
-    sweep = 696 * F + 96 * L + 264 * C
+def b_alg(F, L, C, msg_cam_width=27):
+    """Algorithmic bytes of one synchronous iteration and of the sweep kernel alone.  With the factored
+    keyframe-message layout (18 instead of 27 doubles per message, read + written once) an edge moves 144 B less."""
+    per_edge = 696 - (27 - msg_cam_width) * 8 * 2
+    total = per_edge * F + 264 * L + 744 * C
+    sweep = per_edge * F + 96 * L + 264 * C
     return total, sweep
 
 
@@ -353,9 +355,11 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     t = max_over_ranks(e0.elapsed_time(e1) / 1e3)
     barrier()
     are, energy, nrel = pg.metrics()
-    total_b, _ = b_alg(F, Lm, C)
+    total_b, _ = b_alg(F, Lm, C)                                   # 696 B per factor
     eng = pg.engine
-    _, sweep_b_local = b_alg(eng.F, eng.L, eng.C)
+    _, sweep_b_survey = b_alg(eng.F, eng.L, eng.C)
+    _, sweep_b_local = b_alg(eng.F, eng.L, eng.C, eng.msg_cam_width)   # what this engine's layout has to move
+    total_b_layout, _ = b_alg(F, Lm, C, eng.msg_cam_width)
     tot_ms, sweep_ms = eng.time_iterations(k, True, True, per_kernel=True) if world == 1 else (None, None)
     # sustained: 200 back-to-back iterations (~0.3 s of continuous fp64 + HBM load; the burst above is ~30 ms)
     ks = args.synth_sustained
@@ -376,12 +380,17 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
                            "note": "back-to-back iterations for ~0.3 s; the burst figure above times %d iterations" % k},
              "l2": "7.2 GB streamed per iteration (inputs larger than L2, no flush needed)",
              "gpu_launches": launches, "are_px_after": are, "energy_after": energy, "generate_s": gen_s, "graph_build_s": build_s,
-             "tile_edges": eng.tile_edges, "n_tiles_local": eng.n_tiles, "iteration_captured_in_cuda_graph": bool(captured) or world == 1}
+             "tile_edges": eng.tile_edges, "n_tiles_local": eng.n_tiles, "iteration_captured_in_cuda_graph": bool(captured) or world == 1,
+             "layout": {"msg_cam_doubles": eng.msg_cam_width, "sweep_kernel_build": eng.sweep_variant, "l2_prefetch_tiles": eng.prefetch_tiles,
+                        "algorithmic_bytes_per_iteration_this_layout": total_b_layout,
+                        "note": "factor->keyframe messages are stored with their rank-2 precision factored (18 doubles instead of 27): 144 B per factor less than SURVEY 8(d)'s 696 B; the SURVEY figure is kept for algorithmic_bytes_per_iteration / frac_of_hbm_peak_whole_iteration"}}
     roof = None
     if sweep_ms is not None:
         ach = sweep_b_local / (sweep_ms / k * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "sweep_kernel", "workload": synth["workload"], "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": ach / hbm_peak,
+                "achieved_with_survey_bytes": sweep_b_survey / (sweep_ms / k * 1e-3) / 1e9, "survey_bytes_per_launch": sweep_b_survey,
+                "bytes_note": "achieved = the bytes THIS layout has to move per launch (552 B per factor with factored keyframe messages, 696 B in SURVEY 8(d)) / mean launch duration; achieved_with_survey_bytes uses the 696 B figure and may exceed the peak",
                 "traffic": ncu_traffic(f"sweep_kernel/synthetic_{C}_{Lm}_{F}"), "traffic_source": "profiles/traffic.json (ncu --set full, per launch)",
                 "ms_per_launch": sweep_ms / k,
                 "algorithmic_bytes_per_launch": sweep_b_local,

@@ -50,7 +50,7 @@ class GbpConfig(C.Structure):
 
 
 EXPORTS = [
-    "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes",
+    "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes", "gbp_ba_layout",
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
     "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
@@ -79,6 +79,7 @@ def load():
     lib.gbp_ba_destroy.argtypes = [vp]
     lib.gbp_ba_reset.argtypes = [vp]
     lib.gbp_ba_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.gbp_ba_layout.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gbp_ba_prior_scan.argtypes = [vp, vp]
     lib.gbp_ba_generate_priors.argtypes = [vp, C.c_double, vp]
     lib.gbp_ba_set_priors.argtypes = [vp, vp, vp]

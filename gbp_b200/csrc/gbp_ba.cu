@@ -92,6 +92,8 @@ struct gbp_ba_graph {
     bool robust = false;
     bool priors_set = false;
     int cam_w = CAM_M;   // doubles per stored factor->keyframe message: 27, or 18 with the factored layout (kernel_variant 5)
+    int pf_dist = 0;     // L2 prefetch distance in tiles (auto for large graphs; GBP_PF_DIST overrides)
+    bool auto_large = false;   // kernel_variant 0 on a large graph: factored messages + early issue + L2 prefetch
     bool pdl = false;    // programmatic dependent launch between the kernels of captured iterations (GBP_PDL=1, small graphs)
     long long launches = 0;
 
@@ -156,7 +158,7 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std;
     p.eta_damping = g->cfg.eta_damping; p.beta = g->cfg.beta; p.nstds = g->cfg.Nstds;
     p.num_undamped = g->cfg.num_undamped_iters; p.min_linear = g->cfg.min_linear_iters;
-    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles;
+    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles; p.pf_dist = g->pf_dist;
     return p;
 }
 
@@ -173,7 +175,26 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
         if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "sweep_kernel (programmatic launch): %s", cudaGetErrorString(e));
         return GBP_OK;
     }
-    if (g->cfg.kernel_variant >= 5 && g->cfg.kernel_variant <= 9) {
+    if (g->cfg.kernel_variant == 10) {   // warp-specialised persistent ring (factored messages, 32-edge tiles)
+        static_assert(ring_smem_bytes() <= 227 * 1024, "ring must fit the opt-in shared memory of one SM");
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
+        const int grid = std::min(g->n_tiles, sms);
+        const int block = 32 * (RING_CONSUMERS + 1);
+        if (g->robust) {
+            CU(cudaFuncSetAttribute(sweep_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes()));
+            sweep_ring_kernel<true><<<grid, block, ring_smem_bytes(), g->stream>>>(p);
+        } else {
+            CU(cudaFuncSetAttribute(sweep_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes()));
+            sweep_ring_kernel<false><<<grid, block, ring_smem_bytes(), g->stream>>>(p);
+        }
+        g->launches++;
+        CU(cudaGetLastError());
+        return GBP_OK;
+    }
+    if (g->auto_large || (g->cfg.kernel_variant >= 5 && g->cfg.kernel_variant <= 9)) {
+        // auto_large (kernel_variant 0, more than 8192 tiles) = 7 + far-ahead L2 prefetch: the default for HBM-bound graphs
+        // (10 M-factor graph, same box: 1.257 ms per launch for the r1d kernel with early issue, 0.995 ms for this one);
         // 5 factored keyframe messages (18-double rows; T <= 64 checked at creation); 6 full rows + early issue;
         // 7 factored + early issue; 8 / 9 = 7 / 6 compiled for 7 CTAs of 64 threads per SM (146 registers)
         constexpr int TP = T <= 64 ? T : 64;
@@ -185,7 +206,7 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
             if (g->robust) sweep_kernel<TP, true, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);  \
             else sweep_kernel<TP, false, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);           \
         } while (0)
-        switch (g->cfg.kernel_variant) {
+        switch (g->auto_large ? 7 : g->cfg.kernel_variant) {
             case 5: GBP_LAUNCH_V(0, true, false, fsmem); break;
             case 6: GBP_LAUNCH_V(0, false, true, esmem); break;
             case 7: GBP_LAUNCH_V(0, true, true, fsmem); break;
@@ -224,14 +245,6 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
             sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
         else
             sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
-    } else if (g->n_tiles > 8192 && T <= 64) {
-        // default for large (HBM-bound) graphs: early issue -- no load of the prologue waits for the tile descriptor
-        // (measured on the 10 M-factor graph: 1.186 -> 1.110 ms per launch, 6.34 TB/s of DRAM traffic)
-        constexpr int TP = T <= 64 ? T : 64;
-        if (g->robust)
-            sweep_kernel<TP, true, true, 0, false, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
-        else
-            sweep_kernel<TP, false, true, 0, false, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
     } else if (g->robust) {
         sweep_kernel<T, true, true><<<g->n_tiles, T, smem, g->stream>>>(p);
     } else {
@@ -467,6 +480,11 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         if (T == 128) { delete g; return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
         if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8) g->cam_w = CAM_MF;
     }
+    if (cfg->kernel_variant == 10) {   // the ring kernel works on 32-edge tiles (one consumer warp each), factored messages
+        if (cfg->tile_edges != 0 && cfg->tile_edges != RING_T) { delete g; return fail(GBP_ERR_INVALID, "kernel_variant 10 needs tile_edges 0 or 32"); }
+        T = RING_T;
+        g->cam_w = CAM_MF;
+    }
     g->T = T;
     long long lblock = cfg->lmk_block;
     if (lblock <= 0) lblock = ((long long)L * LMK_B * 8 <= (24LL << 20)) ? std::max(L, 1) : 262144;
@@ -516,6 +534,13 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     {   // experiment switch (round 2 decides the default): early-start dependencies between the kernels of an iteration
         const char* v = getenv("GBP_PDL");
         g->pdl = v && atoi(v) != 0 && g->n_tiles <= 8192 && cfg->kernel_variant == 0;
+        // large graphs stream ~7 GB per sweep: factored keyframe messages (144 B less per edge), no descriptor wait in
+        // the prologue, and every CTA prefetches the streams of the tile ~38 k edges ahead into L2 (A/B on the 10 M-factor
+        // graph: flat optimum between 400 and 750 tiles of 64 edges; 1800 and more thrash L2)
+        g->auto_large = cfg->kernel_variant == 0 && g->n_tiles > 8192 && T <= 64;
+        if (g->auto_large) g->cam_w = CAM_MF;
+        const char* d = getenv("GBP_PF_DIST");
+        g->pf_dist = d ? std::max(0, atoi(d)) : (g->auto_large ? 38400 / T : 0);
     }
     if (g->n_slots >= (1LL << 31)) { delete g; return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
     g->h_slot_of_factor.assign((size_t)F, 0);
@@ -626,6 +651,15 @@ int gbp_ba_destroy(gbp_handle h) {
 int gbp_ba_sizes(gbp_handle h, int64_t out[6]) {
     if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
     out[0] = h->C; out[1] = h->L; out[2] = h->F; out[3] = h->n_tiles; out[4] = h->T; out[5] = h->n_slots;
+    return GBP_OK;
+}
+
+int gbp_ba_layout(gbp_handle h, int64_t out[4]) {
+    if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
+    out[0] = h->cam_w;                 // doubles per stored factor->keyframe message: 27 (full) or 18 (factored)
+    out[1] = h->pf_dist;               // L2 prefetch distance in tiles (0 = off)
+    out[2] = h->auto_large ? 7 : h->cfg.kernel_variant;   // sweep kernel build in use
+    out[3] = h->pdl ? 1 : 0;
     return GBP_OK;
 }
 

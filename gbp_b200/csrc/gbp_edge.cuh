@@ -40,6 +40,7 @@ struct SweepParams {
     double var0, eta_damping, beta, nstds;
     int num_undamped, min_linear, loss, stages;
     int n_tiles;
+    int pf_dist;   // > 0: a CTA also prefetches the streams of tile (its tile + pf_dist) into L2 (early-issue kernels)
 };
 
 // per-edge register inputs fetched straight from global memory

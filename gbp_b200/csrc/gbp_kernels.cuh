@@ -93,6 +93,10 @@ __device__ __forceinline__ double2 ldg_hint(const double2* ptr, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
     return v;
 }
+// L2 prefetch of a contiguous block (16 B aligned, multiple of 16 B): no shared memory, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -207,6 +211,24 @@ __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T
         }
         const int lmk = load_edge_scalars(p, base + tid, r);
         gather_lmk_belief<HINTS>(p, lmk, r);
+        // Far-ahead L2 prefetch: CTAs start roughly in tile order, so the streams of tile + pf_dist are fetched from HBM
+        // now and are L2 hits when that tile's CTA asks for them (its loads then cost an L2 round trip, not a loaded-HBM one)
+        if (p.pf_dist > 0 && tid >= 1 && tid <= 8) {
+            const long long tp = (long long)tile + p.pf_dist;
+            if (tp < p.n_tiles) {
+                const long long b = tp * T;
+                switch (tid) {
+                    case 1: bulk_prefetch_l2(p.msg_cam + b * CW, (uint32_t)T * CW * 8); break;
+                    case 2: bulk_prefetch_l2(p.msg_lmk + b * LMK_M, (uint32_t)T * LMK_M * 8); break;
+                    case 3: bulk_prefetch_l2(p.linpoint + b * 9, (uint32_t)T * 72); break;
+                    case 4: bulk_prefetch_l2(p.z + b * 2, (uint32_t)T * 16); break;
+                    case 5: bulk_prefetch_l2(p.lmk_idx + b, (uint32_t)T * 4); break;
+                    case 6: bulk_prefetch_l2(p.iters + b, (uint32_t)T * 4); break;
+                    case 7: bulk_prefetch_l2(p.flags + b, (uint32_t)T * 4); break;
+                    default: if (ROBUST) bulk_prefetch_l2(p.sigma2a + b, (uint32_t)T * 8); break;
+                }
+            }
+        }
     }
     const Tile tl = p.tiles[tile];
     const int n = tl.count;
@@ -364,6 +386,234 @@ __global__ void __launch_bounds__(T, 256 / T) sweep_kernel_persistent(const Swee
         r_cur = r_next;
     }
     if (tid == 0) bulk_wait_read0();
+}
+
+// ----------------------------------------------------------------------------------------
+// Warp-specialised persistent sweep (kernel_variant 10; factored keyframe messages, 32-edge tiles).
+//
+// One CTA per SM: warp 0 is the PRODUCER, warps 1..RING_CONSUMERS are CONSUMERS, one tile (= one warp of edges) each at a
+// time.  Shared memory is a ring of RING_SLOTS tile slots; a slot holds everything a tile needs -- message rows,
+// linearisation points, the per-edge scalars (landmark index, iters, flags, z, adaptive variance), the gathered
+// landmark belief rows and the keyframe belief row -- so a consumer never waits for global memory: while
+// RING_CONSUMERS slots are being computed, the other slots are in flight (RING_SLOTS - RING_CONSUMERS tiles, ~70 KB per
+// SM: the bandwidth-delay product of HBM3e at ~1.5 us).  The default kernel has 12 warps per SM that each spend a
+// third of their life waiting for their tile (long_scoreboard 2.8 - 4.9 of 9 cycles per instruction, see profiles/).
+//
+//   full_a[slot]  bulk copies of the tile's contiguous streams landed (tx count)        producer -> producer, consumer
+//   full_b[slot]  gather of the 96 B landmark rows (cp.async, needs the indices of
+//                 full_a) and the keyframe row landed; descriptor written               producer -> consumer
+//   empty[slot]   consumer finished: rows stored (bulk store has read the slot)         consumer -> producer
+//
+// The producer issues the gather of tile k - RING_LAG in the same loop iteration as the bulk copies of tile k, so it
+// never blocks on the first round trip of a tile.  Keyframe-side sums: the warp's 27 column sums are formed in
+// registers by a shuffle reduce-scatter (lane c ends with column c), no shared memory.
+// ----------------------------------------------------------------------------------------
+constexpr int RING_T = 32;            // edges per tile (one consumer warp)
+constexpr int RING_SLOTS = 16;
+constexpr int RING_CONSUMERS = 11;    // 12 warps x 32 lanes x 168 registers = the register file
+constexpr int RING_LAG = 3;
+constexpr int RING_BEL_STRIDE = 14;   // doubles per gathered landmark row in the slot (12 + pad: conflict-free 16 B reads)
+
+struct RingSlot {                      // byte offsets inside a slot; every stream starts 16 B aligned
+    static constexpr int MC = 0;                                   // [32][18] factored keyframe messages
+    static constexpr int ML = MC + RING_T * CAM_MF * 8;            // [32][9]
+    static constexpr int LP = ML + RING_T * LMK_M * 8;             // [32][9]
+    static constexpr int BEL = LP + RING_T * 9 * 8;                // [32][14] gathered landmark belief rows
+    static constexpr int Z = BEL + RING_T * RING_BEL_STRIDE * 8;   // [32][2]
+    static constexpr int VAR = Z + RING_T * 16;                    // [32] adaptive variance
+    static constexpr int IDX = VAR + RING_T * 8;                   // [32] i32
+    static constexpr int ITERS = IDX + RING_T * 4;
+    static constexpr int FLAGS = ITERS + RING_T * 4;
+    static constexpr int CB = FLAGS + RING_T * 4;                  // [34] keyframe belief row
+    static constexpr int META = CB + 34 * 8;                       // Tile (count, cam) + pad
+    static constexpr int BYTES = META + 16;
+};
+static_assert(RingSlot::BYTES % 16 == 0, "slots must keep 16 B alignment");
+constexpr size_t ring_smem_bytes() { return (size_t)RING_SLOTS * RingSlot::BYTES + 3 * RING_SLOTS * 8; }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed (counted in the barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Sum of v[0..26] over the 32 lanes of a warp; lane c (< 27) returns column c.  Reduce-scatter butterfly: at distance
+// 16, 8, 4, 2, 1 a lane keeps the half of its columns selected by the corresponding bit of its lane id and adds the
+// partner's copy of that half: 31 doubles exchanged instead of 27 x 5.  Fixed tree => deterministic.
+__device__ __forceinline__ double warp_column_sums27(const double* full, int lane) {
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < CAM_M ? full[k] : 0.0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+            const double keep = up ? v[w + j] : v[j];
+            const double give = up ? v[j] : v[w + j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, give, w);
+        }
+    }
+    return v[0];
+}
+
+template <bool ROBUST>
+__global__ void __launch_bounds__(32 * (RING_CONSUMERS + 1), 1) sweep_ring_kernel(const SweepParams p) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(ring + (size_t)RING_SLOTS * RingSlot::BYTES);
+    uint64_t* full_b = full_a + RING_SLOTS;
+    uint64_t* empty = full_b + RING_SLOTS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int nk = first < p.n_tiles ? (p.n_tiles - first + stride - 1) / stride : 0;   // tiles of this CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RING_SLOTS; ++s) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&full_b[s], 33);      // 32 cp.async completions + the producer's release of the descriptor
+            mbar_init(&empty[s], 1);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        const uint64_t pol_stream = policy_evict_first();
+        const uint64_t pol_keep = policy_evict_last();
+        (void)pol_keep;
+        Tile tl_next{0, 0};
+        if (nk > 0) tl_next = p.tiles[first];
+        constexpr uint32_t BYTES_A = RING_T * (CAM_MF + LMK_M + 9) * 8 + RING_T * (16 + 4 + 4 + 4) + (ROBUST ? RING_T * 8 : 0);
+        for (int k = 0; k < nk + RING_LAG; ++k) {
+            // ---- gather of tile k - LAG (its indices landed long ago)
+            const int kb = k - RING_LAG;
+            if (kb >= 0) {
+                const int slot = kb % RING_SLOTS;
+                unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
+                mbar_wait(&full_a[slot], (uint32_t)((kb / RING_SLOTS) & 1));
+                const int lmk = reinterpret_cast<const int*>(S + RingSlot::IDX)[lane];
+                const double* src = p.lmk_belief + (long long)lmk * LMK_B;
+                double* dst = reinterpret_cast<double*>(S + RingSlot::BEL) + lane * RING_BEL_STRIDE;
+#pragma unroll
+                for (int j = 0; j < LMK_B / 2; ++j) cp_async16(dst + 2 * j, src + 2 * j);
+                cp_async_arrive_noinc(&full_b[slot]);
+                if (lane == 0) mbar_arrive(&full_b[slot]);
+            }
+            // ---- bulk copies of tile k
+            if (k < nk) {
+                const int slot = k % RING_SLOTS, use = k / RING_SLOTS;
+                unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
+                if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+                const int tile = first + k * stride;
+                const long long base = (long long)tile * RING_T;
+                const Tile tl = tl_next;
+                if (k + 1 < nk) tl_next = p.tiles[tile + stride];      // arrives during the coming iterations
+                if (lane == 0) {
+                    *reinterpret_cast<Tile*>(S + RingSlot::META) = tl;
+                    mbar_expect_tx(&full_a[slot], BYTES_A);
+                    bulk_g2s_hint(S + RingSlot::MC, p.msg_cam + base * CAM_MF, RING_T * CAM_MF * 8, &full_a[slot], pol_stream);
+                    bulk_g2s_hint(S + RingSlot::ML, p.msg_lmk + base * LMK_M, RING_T * LMK_M * 8, &full_a[slot], pol_stream);
+                    bulk_g2s_hint(S + RingSlot::LP, p.linpoint + base * 9, RING_T * 72, &full_a[slot], pol_stream);
+                    bulk_g2s(S + RingSlot::Z, p.z + base * 2, RING_T * 16, &full_a[slot]);
+                    bulk_g2s(S + RingSlot::IDX, p.lmk_idx + base, RING_T * 4, &full_a[slot]);
+                    bulk_g2s(S + RingSlot::ITERS, p.iters + base, RING_T * 4, &full_a[slot]);
+                    bulk_g2s(S + RingSlot::FLAGS, p.flags + base, RING_T * 4, &full_a[slot]);
+                    if (ROBUST) bulk_g2s(S + RingSlot::VAR, p.sigma2a + base, RING_T * 8, &full_a[slot]);
+                }
+                // far-ahead L2 prefetch of a later tile's streams (any CTA may own it: L2 is shared)
+                if (p.pf_dist > 0 && lane >= 1 && lane <= 8) {
+                    const long long tp = (long long)tile + p.pf_dist;
+                    if (tp < p.n_tiles) {
+                        const long long b = tp * RING_T;
+                        switch (lane) {
+                            case 1: bulk_prefetch_l2(p.msg_cam + b * CAM_MF, RING_T * CAM_MF * 8); break;
+                            case 2: bulk_prefetch_l2(p.msg_lmk + b * LMK_M, RING_T * LMK_M * 8); break;
+                            case 3: bulk_prefetch_l2(p.linpoint + b * 9, RING_T * 72); break;
+                            case 4: bulk_prefetch_l2(p.z + b * 2, RING_T * 16); break;
+                            case 5: bulk_prefetch_l2(p.lmk_idx + b, RING_T * 4); break;
+                            case 6: bulk_prefetch_l2(p.iters + b, RING_T * 4); break;
+                            case 7: bulk_prefetch_l2(p.flags + b, RING_T * 4); break;
+                            default: if (ROBUST) bulk_prefetch_l2(p.sigma2a + b, RING_T * 8); break;
+                        }
+                    }
+                }
+                // keyframe belief row: 33 doubles, 8 B copies (rows are only 8 B aligned)
+                const double* crow = p.cam_belief + (long long)tl.cam * CAM_B;
+                double* cdst = reinterpret_cast<double*>(S + RingSlot::CB);
+                cp_async8(cdst + lane, crow + lane);
+                if (lane == 0) cp_async8(cdst + 32, crow + 32);
+                // (covered by the cp.async arrive of this tile's gather, RING_LAG iterations from now)
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        for (int k = warp - 1; k < nk; k += RING_CONSUMERS) {
+            const int slot = k % RING_SLOTS;
+            const uint32_t par = (uint32_t)((k / RING_SLOTS) & 1);
+            unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
+            mbar_wait(&full_a[slot], par);
+            mbar_wait(&full_b[slot], par);
+            const Tile tl = *reinterpret_cast<const Tile*>(S + RingSlot::META);
+            const int n = tl.count;
+            const int tile = first + k * stride;
+            const long long base = (long long)tile * RING_T;
+            double* s_mc = reinterpret_cast<double*>(S + RingSlot::MC);
+            double* s_ml = reinterpret_cast<double*>(S + RingSlot::ML);
+            double* s_lp = reinterpret_cast<double*>(S + RingSlot::LP);
+            EdgeRegs r;
+            r.it = reinterpret_cast<const int*>(S + RingSlot::ITERS)[lane];
+            r.fl = reinterpret_cast<const int*>(S + RingSlot::FLAGS)[lane];
+            r.var = ROBUST ? reinterpret_cast<const double*>(S + RingSlot::VAR)[lane] : p.var0;
+            const double2 zz = reinterpret_cast<const double2*>(S + RingSlot::Z)[lane];
+            r.z[0] = zz.x;
+            r.z[1] = zz.y;
+            const double2* b2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(S + RingSlot::BEL) + lane * RING_BEL_STRIDE);
+#pragma unroll
+            for (int j = 0; j < LMK_B / 2; ++j) {
+                const double2 v = b2[j];
+                r.bl[2 * j] = v.x;
+                r.bl[2 * j + 1] = v.y;
+            }
+            double full[CAM_M];
+            bool relin = false;
+            if (lane < n) {
+                relin = edge_sweep<ROBUST, true>(p, base + lane, r, reinterpret_cast<const double*>(S + RingSlot::CB), s_lp + lane * 9,
+                                                 s_mc + lane * CAM_MF, s_ml + lane * LMK_M, full);
+            } else {        // padding lanes add nothing to the keyframe-side sums (zeroed here, not before: registers)
+#pragma unroll
+                for (int j = 0; j < CAM_M; ++j) full[j] = 0.0;
+            }
+            fence_async_smem();      // generic-proxy writes of the new rows -> visible to the bulk-copy engine
+            const unsigned any_relin = __ballot_sync(0xffffffffu, relin);    // also the warp-level barrier before the stores
+            if (lane == 0) {
+                const uint32_t n_even = (uint32_t)((n + 1) & ~1);
+                const uint64_t pol = policy_evict_first();
+                if (p.stages & ST_MESSAGES) {
+                    bulk_s2g_hint(p.msg_cam + base * CAM_MF, s_mc, n_even * CAM_MF * 8, pol);
+                    bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, n_even * LMK_M * 8);
+                }
+                if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, n_even * 72, pol);
+                bulk_commit();
+            }
+            if (p.stages & ST_BELIEFS) {
+                const double col = warp_column_sums27(full, lane);
+                if (lane < CAM_M) p.tile_partial[(long long)tile * CAM_M + lane] = col;
+            }
+            if (lane == 0) {
+                bulk_wait_read0();          // the engine has read the slot
+                mbar_arrive(&empty[slot]);  // ... which every lane of this warp finished using before the ballot above
+            }
+            __syncwarp();
+        }
+    }
 }
 
 template <int T, bool ROBUST>

@@ -60,6 +60,10 @@ class BAEngine:
         sizes = (C.c_int64 * 6)()
         L.check(lib.gbp_ba_sizes(h, sizes))
         self.C, self.L, self.F, self.n_tiles, self.tile_edges, self.n_slots = [int(v) for v in sizes]
+        lay = (C.c_int64 * 4)()
+        L.check(lib.gbp_ba_layout(h, lay))
+        # doubles per stored factor->keyframe message (27 full / 18 factored), L2 prefetch distance, sweep kernel build
+        self.msg_cam_width, self.prefetch_tiles, self.sweep_variant = int(lay[0]), int(lay[1]), int(lay[2])
         self.K4 = K4
         self.device = int(device)
 

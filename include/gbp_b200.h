@@ -55,14 +55,15 @@ typedef struct gbp_config {
     int32_t loss;                /* gbp_loss (gbp/gbp.py:243)                                  */
     int32_t tile_edges;          /* 0 = auto; else 32/64/128 edges per tile (engine tuning)    */
     int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
-    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default; graphs of more than 8192 tiles use its
-                                        early-issue build, = variant 6); 1 = first-version LDG kernel; 2 = TMA, no hints;
+    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default; graphs of more than 8192 tiles use
+                                        variant 7 plus a far-ahead L2 prefetch); 1 = first-version LDG kernel; 2 = TMA, no hints;
                                     3 = 128-register build; 4 = persistent double-buffered (tiles of 32 / 64);
                                     5 = factor->keyframe messages stored with their rank-2 precision factored (eta[6] | W[2][6],
                                         Lambda = W^T W: 144 B less traffic per edge and sweep; tiles of 32 / 64).  GBP_F_MSG_CAM
                                         reads and writes keep the full eta[6] | Lambda[21] form;
                                     6 = early issue: bulk loads, scalars and the landmark gather do not wait for the tile descriptor;
-                                    7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments) */
+                                    7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments);
+                                    10 = warp-specialised persistent ring (experiment, producer-bound: 2x slower) */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */
@@ -121,6 +122,11 @@ int gbp_ba_reset(gbp_handle h);
 
 /* Sizes: C, L, F, number of edge tiles, edges per tile, padded edge slots. */
 int gbp_ba_sizes(gbp_handle h, int64_t out[6]);
+
+/* Engine layout chosen for this graph (no reference counterpart; used by bench.py to count the bytes a sweep moves):
+ * out[0] doubles per stored factor->keyframe message (27 full, 18 factored), out[1] L2 prefetch distance in tiles,
+ * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice), out[3] programmatic launches. */
+int gbp_ba_layout(gbp_handle h, int64_t out[4]);
 
 /* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
  * must be combined across ranks: call gbp_ba_prior_scan first, max-reduce the C doubles it returns

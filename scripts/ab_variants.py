@@ -24,7 +24,7 @@ from gbp_b200.synthetic import make_synthetic  # noqa: E402
 
 CFG = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
 OUT = os.path.join(ROOT, "gpurun_out", "ab_variants.jsonl")
-VARIANTS, PDL = [5, 6, 7, 9], False
+VARIANTS, PDL, PF, RUNS = [5, 6, 7, 9], False, [0], []
 
 
 def emit(d):
@@ -78,8 +78,12 @@ def fr1desk(reps):
 def synthetic(cams, lmks, iters):
     prob = make_synthetic(cams, lmks, 10, seed=0)
     base = None
-    for name, variant in [("default", 0)] + [(f"variant{v}", v) for v in VARIANTS] + [("default_again", 0)]:
+    runs = [("default", 0, 0)] + [(f"variant{v}" + (f"_pf{d}" if d else ""), v, d) for v in VARIANTS for d in PF] + [("default_again", 0, 0)]
+    if RUNS:
+        runs = [("default", 0, 0)] + [(f"variant{v}_pf{d}", v, d) for v, d in RUNS] + [("default_again", 0, 0)]
+    for name, variant, pf in runs:
         try:
+            os.environ["GBP_PF_DIST"] = str(pf)
             g = create_ba_graph(prob, CFG, kernel_variant=variant)
             e = g._eng
             g.generate_priors_var(50.0); g.update_all_beliefs()
@@ -111,9 +115,15 @@ if __name__ == "__main__":
     ap.add_argument("--skip-synthetic", action="store_true")
     ap.add_argument("--variants", default="5,6,7,9")
     ap.add_argument("--pdl", action="store_true")
+    ap.add_argument("--pf", default="0", help="L2 prefetch distances (tiles) to try on the synthetic graph")
+    ap.add_argument("--skip-fr1desk", action="store_true")
+    ap.add_argument("--runs", default="", help="explicit synthetic runs: variant:pf,variant:pf,...")
     a = ap.parse_args()
     VARIANTS = [int(v) for v in a.variants.split(",") if v]
     PDL = a.pdl
-    fr1desk(a.reps)
+    PF = [int(v) for v in a.pf.split(",") if v]
+    RUNS = [tuple(int(x) for x in r.split(":")) for r in a.runs.split(",") if r]
+    if not a.skip_fr1desk:
+        fr1desk(a.reps)
     if not a.skip_synthetic:
         synthetic(a.cams, a.lmks, a.iters)
