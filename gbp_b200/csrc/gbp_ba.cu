@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -439,7 +440,7 @@ int gbp_device_count(void) {
     return n;
 }
 
-int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id,
+static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id,
                   const double* z, const double* cam_mu0, const double* lmk_mu0, const double K[4], int device,
                   void* stream, gbp_handle* out) {
     if (!cfg || !out || !K) return fail(GBP_ERR_INVALID, "null argument");
@@ -457,8 +458,8 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
     }
     CU(cudaSetDevice(device));
-    gbp_ba_graph* g = new (std::nothrow) gbp_ba_graph();
-    if (!g) return fail(GBP_ERR_INVALID, "out of host memory");
+    std::unique_ptr<gbp_ba_graph> owner(new gbp_ba_graph());   // freed on every early return / exception below
+    gbp_ba_graph* g = owner.get();
     g->device = device;
     g->cfg = *cfg;
     g->K = Intrinsics{K[0], K[1], K[2], K[3]};
@@ -468,20 +469,20 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         g->stream = reinterpret_cast<cudaStream_t>(stream);
     } else {
         cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete g; return fail(GBP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { return fail(GBP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         g->own_stream = true;
     }
 
     // ---------------- host graph compiler ----------------
     int T = cfg->tile_edges;
     if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
-    if (T != 32 && T != 64 && T != 128) { delete g; return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
+    if (T != 32 && T != 64 && T != 128) { return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
     if (cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) {
-        if (T == 128) { delete g; return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
+        if (T == 128) { return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
         if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8) g->cam_w = CAM_MF;
     }
     if (cfg->kernel_variant == 10) {   // the ring kernel works on 32-edge tiles (one consumer warp each), factored messages
-        if (cfg->tile_edges != 0 && cfg->tile_edges != RING_T) { delete g; return fail(GBP_ERR_INVALID, "kernel_variant 10 needs tile_edges 0 or 32"); }
+        if (cfg->tile_edges != 0 && cfg->tile_edges != RING_T) { return fail(GBP_ERR_INVALID, "kernel_variant 10 needs tile_edges 0 or 32"); }
         T = RING_T;
         g->cam_w = CAM_MF;
     }
@@ -542,7 +543,7 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
         const char* d = getenv("GBP_PF_DIST");
         g->pf_dist = d ? std::max(0, atoi(d)) : (g->auto_large ? 38400 / T : 0);
     }
-    if (g->n_slots >= (1LL << 31)) { delete g; return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
+    if (g->n_slots >= (1LL << 31)) { return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
     g->h_slot_of_factor.assign((size_t)F, 0);
     {
         std::vector<long long> pos(run_slot);
@@ -578,10 +579,7 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     }
 
     // ---------------- device allocation + upload ----------------
-    auto bail = [&](cudaError_t e, const char* what) {
-        delete g;
-        return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-    };
+    auto bail = [&](cudaError_t e, const char* what) { return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
     cudaError_t e;
     const size_t S = (size_t)g->n_slots;
     for (int pass = 0; pass < 2; ++pass) {   // pass 0 measures, pass 1 carves
@@ -614,10 +612,24 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     if (L > 0 && (e = cudaMemcpyAsync(g->lmk_mu0.p, lmk_mu0, (size_t)L * 24, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload lmk_mu0");
     {
         int rc = gbp_ba_reset(g);
-        if (rc != GBP_OK) { delete g; return rc; }
+        if (rc != GBP_OK) { return rc; }
     }
-    *out = g;
+    *out = owner.release();
     return GBP_OK;
+}
+
+
+// No C++ exception may cross the C ABI: the graph compiler allocates host vectors proportional to the graph.
+int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id,
+                  const double* z, const double* cam_mu0, const double* lmk_mu0, const double K[4], int device,
+                  void* stream, gbp_handle* out) {
+    try {
+        return ba_create_impl(cfg, C, L, F, cam_id, lmk_id, z, cam_mu0, lmk_mu0, K, device, stream, out);
+    } catch (const std::bad_alloc&) {
+        return fail(GBP_ERR_INVALID, "out of host memory while compiling the graph (C=%d L=%d F=%lld)", C, L, (long long)F);
+    } catch (const std::exception& e) {
+        return fail(GBP_ERR_INVALID, "graph compiler: %s", e.what());
+    }
 }
 
 int gbp_ba_reset(gbp_handle h) {
@@ -1015,22 +1027,33 @@ int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_r
     if (ms_total) *ms_total = 0.f;
     if (ms_msg_kernel) *ms_msg_kernel = 0.f;
     if (!per_kernel) {
-        cudaEvent_t e0, e1;
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        struct Pair {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            ~Pair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+        } ev;
+        CU(cudaEventCreate(&ev.e0)); CU(cudaEventCreate(&ev.e1));
         cudaGraphExec_t exec;
         int rc = get_graph(h, st, &exec);
         if (rc != GBP_OK) return rc;
         CU(cudaStreamSynchronize(h->stream));
-        CU(cudaEventRecord(e0, h->stream));
+        CU(cudaEventRecord(ev.e0, h->stream));
         for (int i = 0; i < n_iters; ++i) CU(cudaGraphLaunch(exec, h->stream));
-        CU(cudaEventRecord(e1, h->stream));
-        CU(cudaEventSynchronize(e1));
+        CU(cudaEventRecord(ev.e1, h->stream));
+        CU(cudaEventSynchronize(ev.e1));
         h->launches += 2LL * n_iters;
-        if (ms_total) CU(cudaEventElapsedTime(ms_total, e0, e1));
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ms_total) CU(cudaEventElapsedTime(ms_total, ev.e0, ev.e1));
         return GBP_OK;
     }
-    std::vector<cudaEvent_t> ev((size_t)2 * n_iters + 2);
+    struct Events {      // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    try {
+        evs.v.assign((size_t)2 * n_iters + 2, nullptr);
+    } catch (const std::bad_alloc&) {
+        return fail(GBP_ERR_INVALID, "out of host memory");
+    }
+    std::vector<cudaEvent_t>& ev = evs.v;
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaEventRecord(ev[2 * n_iters], h->stream));
@@ -1053,7 +1076,6 @@ int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_r
     }
     if (ms_total) *ms_total = tot;
     if (ms_msg_kernel) *ms_msg_kernel = acc;
-    for (auto& e : ev) cudaEventDestroy(e);
     return GBP_OK;
 }
 
@@ -1065,8 +1087,10 @@ int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int dev
     if (n == 0) return GBP_OK;
     CU(cudaSetDevice(device));
     DevBuf<double> dx, dh, dj;
-    CU(dx.alloc((size_t)n * 9)); CU(dh.alloc((size_t)n * 2)); CU(dj.alloc((size_t)n * 18));
-    cudaError_t e = cudaMemcpy(dx.p, x, (size_t)n * 72, cudaMemcpyHostToDevice);
+    cudaError_t e = dx.alloc((size_t)n * 9);
+    if (e == cudaSuccess) e = dh.alloc((size_t)n * 2);
+    if (e == cudaSuccess) e = dj.alloc((size_t)n * 18);
+    if (e == cudaSuccess) e = cudaMemcpy(dx.p, x, (size_t)n * 72, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         reprojection_eval_kernel<<<(unsigned)((n + 127) / 128), 128>>>(dx.p, n, Intrinsics{K[0], K[1], K[2], K[3]}, dh.p, dj.p);
         e = cudaGetLastError();
