@@ -43,6 +43,25 @@ UNIT = "msgs/s"
 WORKLOAD = "ba.py --bal_file data/fr1desk.txt (63 keyframes / 2869 landmarks / 13298 reprojection factors), defaults, 200 synchronous iterations"
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver reads ONE JSON line from stdout, but libraries write there too (NCCL prints its version banner on
+    stdout at NCCL_DEBUG=VERSION and WARN).  Keep a private handle on the real stdout and point fd 1 at stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
@@ -151,6 +170,7 @@ def client_loop(graph):
 
 
 def bench_ours(args):
+    protect_stdout()
     import torch
     from gbp_b200 import balio
     from gbp_b200.ba import create_ba_graph
@@ -162,8 +182,8 @@ def bench_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL prints its version banner on STDOUT; keep stdout = one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")           # only a banner; anything NCCL still prints goes to stderr (protect_stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a dedicated non-default stream shared by torch (events, NCCL ordering, L2 flush) and the engine:
     # the default stream's handle is 0, which the C ABI reads as "create your own stream"
@@ -315,7 +335,7 @@ def bench_ours(args):
             "roofline": roofline, "roofline_fr1desk": roof_fr1, "peak_source": peak_src,
             "cpu_baseline": cpu, "synthetic": synth,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if dist is not None:
         # never let a teardown problem hold the box: the numbers are out, leave within 30 s
         import threading

@@ -34,6 +34,15 @@ def test_reference_arm_other_ranks_stay_silent():
     assert res.returncode == 0 and res.stdout.strip() == ""
 
 
+def test_stdout_carries_only_the_json_line():
+    """Libraries (NCCL's version banner) write to fd 1; bench.py keeps a private handle for its one JSON line."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.protect_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('python-level noise'); bench.emit('{\"ok\": 1}')" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout == '{"ok": 1}\n' and "NCCL version" in res.stderr and "python-level noise" in res.stderr
+
+
 def test_build_entry_point():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
