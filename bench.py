@@ -23,6 +23,7 @@ meaningful: `roofline` refers to the sweep kernel on that graph, `roofline_fr1de
 OpenMP on every host thread; the Python reference itself cannot travel to the GPU box) on the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -272,7 +273,9 @@ def bench_ours(args):
     def e2e_run(loop, tag):
         times, means = [], None
         for it in range(args.warmup + args.steps):
+            gc.collect()                      # graphs of earlier steps (proxy objects, pinned blocks) die here, untimed
             flush_buf.zero_(); barrier()
+            gc.disable()                      # like timeit: no collector pause inside the timed region
             t0 = time.perf_counter()
             p2 = balio.BALProblem(pinned["cam_id"], pinned["lmk_id"], pinned["z"], pinned["cam"], pinned["lmk"], prob.K4)
             g2 = create_ba_graph(p2, CFG, device=local, stream=stream)
@@ -283,6 +286,7 @@ def bench_ours(args):
             means = loop(g2)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            gc.enable()
             if os.environ.get("GBP_BENCH_DEBUG"):
                 print(f"[{tag} {it}] create {1e3 * (t1 - t0):.2f} ms  priors {1e3 * (t2 - t1):.2f}  loop {1e3 * (t0 + dt - t2):.2f}  total {1e3 * dt:.2f}", file=sys.stderr)
             g2.close()
