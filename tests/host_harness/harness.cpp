@@ -227,6 +227,13 @@ void hs_iterate(void* hv, int n, int robustify, int local_relin) {
     }
 }
 
+// one stage set at a time (gbp_ba_sweep_local): GBP_STAGE_* bits; the belief stage = keyframe sums + beliefs
+void hs_sweep(void* hv, int stages) {
+    HostSweep* h = static_cast<HostSweep*>(hv);
+    h->sweep(stages);
+    if (stages & ST_BELIEFS) h->beliefs();
+}
+
 void hs_fill_iters(void* hv, int v) {
     HostSweep* h = static_cast<HostSweep*>(hv);
     std::fill(h->iters.begin(), h->iters.end(), v);

@@ -61,5 +61,6 @@ def test_sass_uses_the_bulk_copy_engine():
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "gbp_b200", "lib", "libgbp_b200.so")], capture_output=True,
                           text=True, check=True).stdout
     assert "UBLKCP.S.G" in sass and "UBLKCP.G.S" in sass and "SYNCS.ARRIVE.TRANS64" in sass
+    assert "UBLKPF.L2" in sass          # cp.async.bulk.prefetch.L2: the far-ahead prefetch of the large-graph build
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "gbp_b200", "lib", "libgbp_b200.so")],
                                        capture_output=True, text=True).stdout

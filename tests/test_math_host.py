@@ -42,7 +42,7 @@ def hh():
     lib.hs_generate_priors.argtypes = lib.hs_scale_priors.argtypes = [vp, C.c_double]
     lib.hs_update_beliefs.argtypes = [vp]
     lib.hs_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
-    lib.hs_fill_iters.argtypes = [vp, C.c_int]
+    lib.hs_fill_iters.argtypes = lib.hs_sweep.argtypes = [vp, C.c_int]
     lib.hs_metrics.argtypes = [vp, vp]
     lib.hs_read.argtypes = lib.hs_read_int.argtypes = [vp, C.c_int, vp]
     lib.hs_set_factored.argtypes = [vp, C.c_int]
@@ -311,3 +311,27 @@ def test_edge_sweep_synthetic_small(hh):
     assert np.array_equal(nrel, G["n_relin"])
     assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6 and max(worst) < 1e-5
     s.close()
+
+
+@pytest.mark.parametrize("factored", [False, True], ids=["full", "factored"])
+def test_staged_calls_equal_one_sweep(hh, factored):
+    """robustify_all_factors / relinearise_factors / compute_all_messages / update_all_beliefs one by one
+    (gbp/gbp.py:82-92, the stage bits of gbp_ba_sweep_local) leave the same state as the fused per-edge pass."""
+    G = load_golden("fr1desk_vsmall_huber")
+    cfg = golden_configs(G)
+    a, b = HostSweep(hh, G, cfg, factored), HostSweep(hh, G, cfg, factored)
+    for s in (a, b):
+        hh.hs_generate_priors(s.h, 50.0)
+        hh.hs_update_beliefs(s.h)
+    ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING = 1, 2, 4, 8, 16
+    for i in range(20):
+        if i == 3:
+            hh.hs_fill_iters(a.h, 7); hh.hs_fill_iters(b.h, 7)          # make relinearisation fire early
+        hh.hs_iterate(a.h, 1, 1, 1)
+        for st in (ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES | ST_LOCAL_DAMPING, ST_BELIEFS):
+            hh.hs_sweep(b.h, st)
+    for field, rows, w in ((0, a.C, 33), (1, a.L, 12), (4, a.F, 27), (5, a.F, 9), (6, a.F, 9), (9, a.F, 1)):
+        assert relerr(b.read(field, rows, w), a.read(field, rows, w)) < 1e-12, field
+    assert np.array_equal(a.read_int(7), b.read_int(7)) and np.array_equal(a.read_int(8), b.read_int(8))
+    assert (a.read_int(7) < 17).any()
+    a.close(); b.close()
