@@ -358,7 +358,7 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
     gen_s = time.perf_counter() - t0
     t0 = time.perf_counter()
     pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=local, stream=stream, dist=dist,
-                            torch_stream=torch.cuda.current_stream())
+                            torch_stream=torch.cuda.current_stream(), p2p=args.p2p or None)
     build_s = time.perf_counter() - t0
     pg.generate_priors_var(CFG["prior_std_weaker_factor"])
     pg.update_all_beliefs()
@@ -405,6 +405,7 @@ def bench_synthetic(args, torch, dist, rank, world, local, stream, hbm_peak, bar
              "l2": "7.2 GB streamed per iteration (inputs larger than L2, no flush needed)",
              "gpu_launches": launches, "are_px_after": are, "energy_after": energy, "generate_s": gen_s, "graph_build_s": build_s,
              "tile_edges": eng.tile_edges, "n_tiles_local": eng.n_tiles, "iteration_captured_in_cuda_graph": bool(captured) or world == 1,
+             "exchange": None if world == 1 else ("peer-memory kernels (gbp_ba_p2p_*)" if pg.p2p else "NCCL all-gather"),
              "layout": {"msg_cam_doubles": eng.msg_cam_width, "sweep_kernel_build": eng.sweep_variant, "l2_prefetch_tiles": eng.prefetch_tiles,
                         "algorithmic_bytes_per_iteration_this_layout": total_b_layout,
                         "note": "factor->keyframe messages are stored with their rank-2 precision factored (18 doubles instead of 27): 144 B per factor less than SURVEY 8(d)'s 696 B; the SURVEY figure is kept for algorithmic_bytes_per_iteration / frac_of_hbm_peak_whole_iteration"}}
@@ -502,6 +503,7 @@ def main():
     ap.add_argument("--no-synthetic", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-capture", action="store_true", help="multi-GPU: do not capture the iteration in a CUDA graph")
+    ap.add_argument("--p2p", action="store_true", help="multi-GPU: peer-memory exchange kernels instead of the NCCL all-gather (experimental)")
     ap.add_argument("--synth-cams", type=int, default=1000)
     ap.add_argument("--synth-lmks", type=int, default=1_000_000)
     ap.add_argument("--synth-iters", type=int, default=20)

@@ -52,7 +52,7 @@ class GbpConfig(C.Structure):
 EXPORTS = [
     "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes", "gbp_ba_layout",
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
-    "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
+    "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_p2p_init", "gbp_ba_p2p_attach", "gbp_ba_p2p_scatter", "gbp_ba_p2p_gather_update", "gbp_ba_p2p_status", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
     "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
 ]
@@ -87,6 +87,11 @@ def load():
     lib.gbp_ba_sweep_local.argtypes = [vp, C.c_int]
     lib.gbp_ba_landmark_update.argtypes = [vp]
     lib.gbp_ba_cam_update.argtypes = [vp, vp, C.c_int]
+    lib.gbp_ba_p2p_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.gbp_ba_p2p_attach.argtypes = [vp, vp]
+    lib.gbp_ba_p2p_scatter.argtypes = [vp]
+    lib.gbp_ba_p2p_gather_update.argtypes = [vp]
+    lib.gbp_ba_p2p_status.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gbp_ba_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.gbp_ba_update_beliefs.argtypes = [vp]
     lib.gbp_ba_metrics.argtypes = [vp, dp]

@@ -108,6 +108,14 @@ struct gbp_ba_graph {
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
+    // peer-memory exchange (gbp_ba_p2p_*): own buffer, the peers' buffers as mapped here, device table of the bases
+    char* xchg = nullptr;
+    size_t xchg_bytes = 0;
+    std::vector<char*> peer_map;
+    char** peer_tab_dev = nullptr;
+    int p2p_rank = -1, p2p_nranks = 0;
+    long long p2p_flags_off = 0, p2p_slots_off = 0;
+
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
     Arena arena;
     cudaEvent_t snap_event = nullptr;
@@ -125,6 +133,10 @@ struct gbp_ba_graph {
         cam_belief.release(); lmk_belief.release(); cam_prior.release(); lmk_prior.release(); cam_partial.release();
         tile_partial.release(); tile_metric.release(); metric_out.release(); edge_max.release();
         tile_max.release(); cam_max.release(); cam_mu0.release(); lmk_mu0.release();
+        for (int r = 0; r < (int)peer_map.size(); ++r)
+            if (peer_map[r] && r != p2p_rank) cudaIpcCloseMemHandle(peer_map[r]);
+        if (peer_tab_dev) cudaFree(peer_tab_dev);
+        if (xchg) cudaFree(xchg);
         if (arena.base) cudaFree(arena.base);
         if (snap_event) cudaEventDestroy(snap_event);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -759,6 +771,94 @@ int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {
     cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p, h->cam_mu.p);
     h->launches++;
     CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+namespace {
+P2PParams p2p_params(gbp_ba_graph* h) {
+    P2PParams p{};
+    p.peers = h->peer_tab_dev; p.mine = h->xchg; p.cam_partial = h->cam_partial.p; p.cam_prior = h->cam_prior.p;
+    p.cam_belief = h->cam_belief.p; p.cam_mu = h->cam_mu.p; p.rank = h->p2p_rank; p.nranks = h->p2p_nranks; p.C = h->C;
+    p.n_cta = (h->C + 3) / 4; p.flags_off = h->p2p_flags_off; p.slots_off = h->p2p_slots_off;
+    return p;
+}
+}  // namespace
+
+int gbp_ba_p2p_init(gbp_handle h, int rank, int nranks, void* ipc_handle_out) {
+    CHECK_H(h);
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || !ipc_handle_out) return fail(GBP_ERR_INVALID, "bad rank / nranks / handle pointer");
+    if (h->xchg) return fail(GBP_ERR_STATE, "peer exchange already initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GBP_IPC_HANDLE_BYTES, "GBP_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+    const size_t n_cta = (size_t)(h->C + 3) / 4;
+    h->p2p_flags_off = sizeof(P2PHeader);
+    const size_t flags = Arena::round_up(2 * (size_t)nranks * std::max<size_t>(n_cta, 1) * sizeof(unsigned int));
+    h->p2p_slots_off = (long long)(h->p2p_flags_off + flags);
+    h->xchg_bytes = (size_t)h->p2p_slots_off + 2 * (size_t)nranks * std::max<size_t>((size_t)h->C, 1) * CAM_M * sizeof(double);
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->xchg), h->xchg_bytes));      // its own allocation: IPC handles name whole allocations
+    CU(cudaMemset(h->xchg, 0, h->xchg_bytes));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->xchg));
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    h->p2p_rank = rank;
+    h->p2p_nranks = nranks;
+    return GBP_OK;
+}
+
+int gbp_ba_p2p_attach(gbp_handle h, const void* ipc_handles) {
+    CHECK_H(h);
+    if (!h->xchg) return fail(GBP_ERR_STATE, "call gbp_ba_p2p_init first");
+    if (!ipc_handles) return fail(GBP_ERR_INVALID, "null handles");
+    if (!h->peer_map.empty()) return fail(GBP_ERR_STATE, "peers already attached");
+    try {
+        h->peer_map.assign((size_t)h->p2p_nranks, nullptr);
+    } catch (const std::bad_alloc&) {
+        return fail(GBP_ERR_INVALID, "out of host memory");
+    }
+    for (int r = 0; r < h->p2p_nranks; ++r) {
+        if (r == h->p2p_rank) { h->peer_map[r] = h->xchg; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof(hd), sizeof(hd));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink needed)", r, cudaGetErrorString(e));
+        h->peer_map[r] = static_cast<char*>(ptr);
+    }
+    CU(cudaMalloc(reinterpret_cast<void**>(&h->peer_tab_dev), (size_t)h->p2p_nranks * sizeof(char*)));
+    CU(cudaMemcpy(h->peer_tab_dev, h->peer_map.data(), (size_t)h->p2p_nranks * sizeof(char*), cudaMemcpyHostToDevice));
+    return GBP_OK;
+}
+
+int gbp_ba_p2p_scatter(gbp_handle h) {
+    CHECK_H(h);
+    if (!h->peer_tab_dev) return fail(GBP_ERR_STATE, "peer exchange not attached");
+    if (h->C == 0) return GBP_OK;
+    p2p_scatter_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(p2p_params(h));
+    h->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+int gbp_ba_p2p_gather_update(gbp_handle h) {
+    CHECK_H(h);
+    if (!h->peer_tab_dev) return fail(GBP_ERR_STATE, "peer exchange not attached");
+    if (h->C == 0) return GBP_OK;
+    p2p_gather_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(p2p_params(h));
+    h->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
+int gbp_ba_p2p_status(gbp_handle h, int64_t out[2]) {
+    CHECK_H(h);
+    if (!out) return fail(GBP_ERR_INVALID, "null out");
+    out[0] = out[1] = 0;
+    if (!h->xchg) return GBP_OK;
+    P2PHeader hd;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(&hd, h->xchg, sizeof(hd), cudaMemcpyDeviceToHost));
+    out[0] = hd.epoch;       // exchanges completed
+    out[1] = hd.timeouts;    // flag waits that gave up (a peer died or never launched its scatter)
     return GBP_OK;
 }
 

@@ -8,6 +8,12 @@ ranks exchange those partial sums with ONE all-gather (NCCL over NVLink / NVSwit
 CPU tests); every rank then adds prior + the partials in rank order, so the keyframe beliefs are
 bit-identical everywhere.  ARE / energy need a 3-scalar all-reduce only when the client asks.
 
+Opt-in (`p2p=True` or GBP_P2P=1): the exchange without a collective call.  Every rank writes its partial sums
+straight into the other ranks' exchange buffers over NVLink (CUDA IPC mappings of one small buffer per rank) and
+raises per-CTA flags there; the keyframe update kernel waits on the flags of its own buffer (`gbp_ba_p2p_*`,
+kernels `p2p_scatter_kernel` / `p2p_gather_update_kernel`).  Same rank-ordered sum, so the same bits.  This path
+is built and reviewed but has not had its hardware run yet; the NCCL all-gather stays the default.
+
 The reference has no distributed code; this is new functionality behind the same
 `synchronous_iteration` surface.
 
@@ -85,6 +91,23 @@ class CudaEngineAdapter:
     def apply_gathered(self, gathered, world):
         self.eng.cam_update(gathered.data_ptr(), world)
 
+    # ---- peer-memory exchange (opt-in)
+    def p2p_setup(self, rank, world, dist):
+        handle = self.eng.p2p_init(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)        # 64-byte CUDA IPC handles, rank order
+        self.eng.p2p_attach(handles)
+        dist.barrier()                                  # everybody mapped everybody before the first store
+
+    def p2p_scatter(self):
+        self.eng.p2p_scatter()
+
+    def p2p_gather_update(self):
+        self.eng.p2p_gather_update()
+
+    def p2p_status(self):
+        return self.eng.p2p_status()
+
     def iterate_single(self, robustify, local_relin):
         self.eng.iterate(1, robustify=robustify, local_relin=local_relin)
 
@@ -112,8 +135,11 @@ class PartitionedBAGraph:
     """`synchronous_iteration` / `generate_priors_var` / `are` / `energy` over a landmark-partitioned graph."""
 
     def __init__(self, prob: BALProblem, configs, rank=0, world=1, device=0, stream=None, dist=None,
-                 engine_factory=None, torch_stream=None, **engine_kw):
+                 engine_factory=None, torch_stream=None, p2p=None, **engine_kw):
         engine_kw_stream = torch_stream
+        if p2p is None:
+            import os
+            p2p = os.environ.get("GBP_P2P", "0") not in ("", "0")
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs an initialised torch.distributed module")
         self.rank, self.world, self.dist = rank, world, dist
@@ -122,6 +148,11 @@ class PartitionedBAGraph:
         factory = engine_factory or (lambda s, c: CudaEngineAdapter(s, c, device, stream, **engine_kw))
         self.adapter = factory(sub, configs)
         self._gather = self.adapter.new_gather_buffer(world) if world > 1 else None
+        self.p2p = bool(p2p) and world > 1
+        if self.p2p:
+            if not hasattr(self.adapter, "p2p_setup"):
+                raise ValueError("this engine has no peer-memory exchange (p2p=True needs the CUDA engine)")
+            self.adapter.p2p_setup(rank, world, dist)
         self._graphs = {}        # stages -> captured CUDA graph of [local sweep, all-gather, keyframe update]
         self._torch_stream = engine_kw_stream
 
@@ -134,6 +165,11 @@ class PartitionedBAGraph:
         """keyframe partial sums -> all ranks (one all-gather); the landmark beliefs, which need no communication, are
         updated on the compute stream while the collective is in flight; then prior + partials in rank order."""
         a = self.adapter
+        if self.p2p:
+            a.p2p_scatter()             # partial sums -> every peer's buffer (stores over NVLink) + flags
+            a.landmark_update()         # overlaps the transfer
+            a.p2p_gather_update()       # waits on this rank's flags; prior + sums in rank order
+            return
         work = self.dist.all_gather_into_tensor(self._gather, a.partial_tensor(), async_op=True)
         a.landmark_update()
         work.wait()
@@ -236,4 +272,8 @@ class PartitionedBAGraph:
             import torch
             torch.cuda.synchronize()
             self._graphs.clear()
+        if self.p2p:
+            import torch
+            torch.cuda.synchronize()
+            self.dist.barrier()          # nobody still writes into a buffer that is about to be freed
         self.adapter.close()

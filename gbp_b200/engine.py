@@ -111,6 +111,29 @@ class BAEngine:
         L.check(self._lib.gbp_ba_cam_update(self._h, C.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
                                             int(nranks)))
 
+    # ------------------------------------------------------------------ peer-memory exchange (multi-GPU, opt-in)
+    def p2p_init(self, rank, nranks):
+        """Allocate this rank's exchange buffer; returns its CUDA IPC handle (bytes) for the other ranks."""
+        buf = C.create_string_buffer(64)
+        L.check(self._lib.gbp_ba_p2p_init(self._h, int(rank), int(nranks), buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """`handles`: the IPC handles of all ranks in rank order (own entry ignored)."""
+        blob = b"".join(handles)
+        L.check(self._lib.gbp_ba_p2p_attach(self._h, C.c_char_p(blob)))
+
+    def p2p_scatter(self):
+        L.check(self._lib.gbp_ba_p2p_scatter(self._h))
+
+    def p2p_gather_update(self):
+        L.check(self._lib.gbp_ba_p2p_gather_update(self._h))
+
+    def p2p_status(self):
+        out = (C.c_int64 * 2)()
+        L.check(self._lib.gbp_ba_p2p_status(self._h, out))
+        return int(out[0]), int(out[1])
+
     def iterate(self, n_iters=1, robustify=False, local_relin=True):
         L.check(self._lib.gbp_ba_iterate(self._h, int(n_iters), int(bool(robustify)), int(bool(local_relin))))
 

@@ -152,6 +152,24 @@ int gbp_ba_landmark_update(gbp_handle h);
  * doubles (e.g. the output of an NCCL all-gather of GBP_F_CAM_PARTIAL); NULL = use this handle's own
  * partial (single GPU). */
 int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks);
+
+/* Peer-memory exchange of the keyframe partial sums (multi-GPU, one process per GPU; no reference counterpart).
+ * Opt-in replacement of [all-gather -> gbp_ba_cam_update]: every rank writes its C x 27 partial sums straight into
+ * the other ranks' exchange buffers over NVLink (CUDA IPC mappings) and raises a per-CTA flag there; the update
+ * kernel of each rank waits for the flags of its own buffer and adds prior + sums in rank order.
+ *   gbp_ba_p2p_init    allocates this rank's buffer and returns its CUDA IPC handle (GBP_IPC_HANDLE_BYTES bytes);
+ *   gbp_ba_p2p_attach  maps the buffers of all ranks (handles in rank order, own entry ignored);
+ *   per iteration:     gbp_ba_sweep_local(h, stages | GBP_STAGE_DEFER_LANDMARKS); gbp_ba_p2p_scatter(h);
+ *                      gbp_ba_landmark_update(h);  gbp_ba_p2p_gather_update(h);
+ *   gbp_ba_p2p_status  out[0] = exchanges completed, out[1] = waits that timed out (~2 s; a peer is gone).
+ * Every rank must destroy its handle only after all ranks stopped iterating (barrier on the host side).
+ * Status of this path: built and reviewed, NOT yet run on hardware (round 2). */
+#define GBP_IPC_HANDLE_BYTES 64
+int gbp_ba_p2p_init(gbp_handle h, int rank, int nranks, void* ipc_handle_out);
+int gbp_ba_p2p_attach(gbp_handle h, const void* ipc_handles);
+int gbp_ba_p2p_scatter(gbp_handle h);
+int gbp_ba_p2p_gather_update(gbp_handle h);
+int gbp_ba_p2p_status(gbp_handle h, int64_t out[2]);
 /* n x synchronous_iteration(robustify, local_relin) on one GPU (gbp/gbp.py:86-92; the loop of
  * ba.py:84-105 without the client's per-iteration reads): sweep_local + cam_update, replayed from a
  * CUDA graph. */

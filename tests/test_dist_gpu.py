@@ -14,7 +14,7 @@ CFG = dict(gauss_noise_std=2, loss=None, Nstds=3.0, beta=0.01, num_undamped_iter
            eta_damping=0.4, prior_std_weaker_factor=50.0)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, p2p=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -26,7 +26,8 @@ def _worker(rank, world, port, out_dir):
     from gbp_b200.dist import PartitionedBAGraph
     from gbp_b200.synthetic import make_synthetic
     prob = make_synthetic(40, 6000, 8, seed=5)
-    pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=rank, stream=s.cuda_stream, dist=dist, torch_stream=s)
+    pg = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=rank, stream=s.cuda_stream, dist=dist, torch_stream=s,
+                            p2p=p2p)
     pg.generate_priors_var(50.0)
     pg.update_all_beliefs()
     trace = []
@@ -39,12 +40,16 @@ def _worker(rank, world, port, out_dir):
         else:
             pg.synchronous_iteration(robustify=True, local_relin=True)
     trace.append(pg.metrics())
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace))
+    status = pg.adapter.p2p_status() if p2p else (0, 0)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace), p2p_status=np.array(status))
     pg.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_partition_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("p2p", [False, pytest.param(True, marks=pytest.mark.skipif(
+    os.environ.get("GBP_TEST_EXPERIMENTAL", "0") in ("", "0"),
+    reason="peer-memory exchange kernels: not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1"))], ids=["nccl", "p2p"])
+def test_two_gpu_partition_matches_single_gpu(tmp_path, p2p):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -54,9 +59,11 @@ def test_two_gpu_partition_matches_single_gpu(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), p2p), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     assert np.array_equal(r0["means"], r1["means"]) and np.array_equal(r0["trace"], r1["trace"])
+    if p2p:      # one exchange per belief update (1 initial + 25 iterations + capture's eager one), no wait timed out
+        assert r0["p2p_status"][0] >= 26 and r0["p2p_status"][1] == 0 and r1["p2p_status"][1] == 0
     prob = make_synthetic(40, 6000, 8, seed=5)
     pg = PartitionedBAGraph(prob, CFG)
     pg.generate_priors_var(50.0)
