@@ -54,7 +54,7 @@ EXPORTS = [
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
     "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_p2p_init", "gbp_ba_p2p_attach", "gbp_ba_p2p_scatter", "gbp_ba_p2p_gather_update", "gbp_ba_p2p_status", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
-    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
+    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_plan_create", "gbp_plan_sizes", "gbp_plan_copy", "gbp_plan_destroy", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
 ]
 
 _lib = None
@@ -114,6 +114,11 @@ def load():
     lib.gbp_ba_launch_count.argtypes = [vp]
     lib.gbp_ba_launch_count.restype = C.c_int64
     lib.gbp_reprojection_eval.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp]
+    lib.gbp_plan_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp, C.POINTER(vp)]
+    lib.gbp_plan_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.gbp_plan_copy.argtypes = [vp] * 10
+    lib.gbp_plan_destroy.argtypes = [vp]
+    lib.gbp_plan_destroy.restype = None
     lib.gbp_bal_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.gbp_bal_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gbp_bal_copy.argtypes = [vp, vp, vp, vp, vp, vp, vp]

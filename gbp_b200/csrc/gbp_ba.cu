@@ -436,6 +436,130 @@ int iteration_stages(int robustify, int local_relin) {
     return st;
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Host graph compiler: measurement list -> engine storage order.  Pure host code (no CUDA call), so it is also
+// exported on its own (gbp_plan_*) and tested on CPU.  Replaces the construction loops of create_ba_graph
+// (gbp/gbp_ba.py:128-143), which are O(C F) in the reference.
+//   factor order  = stable sort of the measurements by camera (the order the reference creates its factors in)
+//   storage order = runs of equal (landmark block, camera), factor order inside a run; every run is cut into tiles of
+//                   <= T edges, a tile owns T consecutive slots, padding only at the end of a run's last tile
+// ----------------------------------------------------------------------------------------
+struct GraphPlan {
+    int T = 32;
+    long long lblock = 1;
+    std::vector<Tile> tiles;
+    std::vector<int> slot_of_factor, file_of_factor, adj;      // factor order; adj = (camera, landmark) pairs
+    std::vector<int> lmk_idx;                                  // [slots] landmark of the edge in that slot (0 in padding)
+    std::vector<double> z;                                     // [slots][2] (only when measurements were given)
+    std::vector<int> lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
+    long long n_slots() const { return (long long)tiles.size() * T; }
+};
+
+// tile_edges / lmk_block: 0 = automatic (same rules for every caller)
+int choose_tiling(int tile_edges, long long lmk_block, int L, int64_t F, int* T_out, long long* lblock_out) {
+    int T = tile_edges;
+    if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
+    if (T != 32 && T != 64 && T != 128) return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128");
+    long long lblock = lmk_block;
+    if (lblock <= 0) lblock = ((long long)L * LMK_B * 8 <= (24LL << 20)) ? std::max(L, 1) : 262144;
+    *T_out = T;
+    *lblock_out = lblock;
+    return GBP_OK;
+}
+
+int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id, const double* z,
+               GraphPlan* plan) {
+    for (int64_t f = 0; f < F; ++f) {
+        if (cam_id[f] < 0 || cam_id[f] >= C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)f, cam_id[f]);
+        if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
+    }
+    plan->T = T;
+    plan->lblock = lblock;
+    const long long nb = L > 0 ? (L + lblock - 1) / lblock : 1;
+
+    // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130)
+    std::vector<long long> cam_start((size_t)C + 1, 0);
+    for (int64_t i = 0; i < F; ++i) cam_start[cam_id[i] + 1]++;
+    for (int c = 0; c < C; ++c) cam_start[c + 1] += cam_start[c];
+    plan->file_of_factor.assign((size_t)F, 0);
+    {
+        std::vector<long long> pos(cam_start.begin(), cam_start.end() - 1);
+        for (int64_t i = 0; i < F; ++i) plan->file_of_factor[(size_t)pos[cam_id[i]]++] = (int)i;
+    }
+    plan->adj.assign((size_t)F * 2, 0);
+    for (int64_t f = 0; f < F; ++f) {
+        const int i = plan->file_of_factor[(size_t)f];
+        plan->adj[2 * f] = cam_id[i];
+        plan->adj[2 * f + 1] = lmk_id[i];
+    }
+    // storage order: (landmark block, camera) runs, factor order inside a run
+    const size_t nkeys = (size_t)nb * (size_t)std::max(C, 1);
+    std::vector<long long> run_start(nkeys + 1, 0);
+    auto key_of = [&](int64_t f) { return (size_t)(plan->adj[2 * f + 1] / lblock) * (size_t)C + (size_t)plan->adj[2 * f]; };
+    for (int64_t f = 0; f < F; ++f) run_start[key_of(f) + 1]++;
+    // tiles per run
+    std::vector<Tile>& tiles = plan->tiles;
+    tiles.clear();
+    std::vector<long long> run_slot(nkeys, 0);
+    {
+        long long tcount = 0;
+        for (size_t k = 0; k < nkeys; ++k) {
+            const long long cnt = run_start[k + 1];
+            run_slot[k] = tcount * T;
+            long long left = cnt;
+            while (left > 0) {
+                Tile t;
+                t.cam = (int)(k % (size_t)std::max(C, 1));
+                t.count = (int)std::min<long long>(left, T);
+                tiles.push_back(t);
+                left -= t.count;
+                ++tcount;
+            }
+        }
+    }
+    const long long n_slots = plan->n_slots();
+    if (n_slots >= (1LL << 31)) return fail(GBP_ERR_INVALID, "graph too large for int32 slots");
+    plan->slot_of_factor.assign((size_t)F, 0);
+    {
+        std::vector<long long> pos(run_slot);
+        for (int64_t f = 0; f < F; ++f) plan->slot_of_factor[(size_t)f] = (int)pos[key_of(f)]++;
+        // runs are contiguous in slots except for the padding of their last tile, which lies at
+        // the END of the run, so consecutive positions are correct.
+    }
+    // slot-ordered inputs
+    plan->lmk_idx.assign((size_t)n_slots, 0);
+    plan->z.assign(z ? (size_t)n_slots * 2 : 0, 0.0);
+    for (int64_t f = 0; f < F; ++f) {
+        const size_t s = (size_t)plan->slot_of_factor[(size_t)f];
+        const int i = plan->file_of_factor[(size_t)f];
+        plan->lmk_idx[s] = plan->adj[2 * f + 1];
+        if (z) {
+            plan->z[2 * s] = z[2 * (size_t)i];
+            plan->z[2 * s + 1] = z[2 * (size_t)i + 1];
+        }
+    }
+    // CSR by landmark over slots (factor order inside a landmark = adj_factors order)
+    plan->lmk_ptr.assign((size_t)L + 1, 0);
+    plan->lmk_slots.assign((size_t)F, 0);
+    for (int64_t f = 0; f < F; ++f) plan->lmk_ptr[(size_t)plan->adj[2 * f + 1] + 1]++;
+    for (int l = 0; l < L; ++l) plan->lmk_ptr[l + 1] += plan->lmk_ptr[l];
+    {
+        std::vector<int> pos(plan->lmk_ptr.begin(), plan->lmk_ptr.end() - 1);
+        for (int64_t f = 0; f < F; ++f) plan->lmk_slots[(size_t)pos[plan->adj[2 * f + 1]]++] = plan->slot_of_factor[(size_t)f];
+    }
+    // CSR by camera over tiles
+    plan->cam_tile_ptr.assign((size_t)C + 1, 0);
+    plan->cam_tiles.assign(tiles.size(), 0);
+    for (const Tile& t : tiles) plan->cam_tile_ptr[(size_t)t.cam + 1]++;
+    for (int c = 0; c < C; ++c) plan->cam_tile_ptr[c + 1] += plan->cam_tile_ptr[c];
+    {
+        std::vector<int> pos(plan->cam_tile_ptr.begin(), plan->cam_tile_ptr.end() - 1);
+        for (size_t t = 0; t < tiles.size(); ++t) plan->cam_tiles[(size_t)pos[tiles[t].cam]++] = (int)t;
+    }
+    return GBP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -465,10 +589,6 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     if (gbp_device_count() <= 0)
         return fail(GBP_ERR_NO_DEVICE, "no CUDA device visible: gbp_b200 has no CPU fallback for the BA sweep");
     if (device < 0 || device >= gbp_device_count()) return fail(GBP_ERR_INVALID, "device %d out of range", device);
-    for (int64_t f = 0; f < F; ++f) {
-        if (cam_id[f] < 0 || cam_id[f] >= C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)f, cam_id[f]);
-        if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
-    }
     CU(cudaSetDevice(device));
     std::unique_ptr<gbp_ba_graph> owner(new gbp_ba_graph());   // freed on every early return / exception below
     gbp_ba_graph* g = owner.get();
@@ -486,9 +606,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     }
 
     // ---------------- host graph compiler ----------------
-    int T = cfg->tile_edges;
-    if (T == 0) T = F >= 64LL * 148 * 6 ? 64 : 32;   // measured: 64-edge tiles beat 128 on large graphs; 32 spreads small ones
-    if (T != 32 && T != 64 && T != 128) { return fail(GBP_ERR_INVALID, "tile_edges must be 0, 32, 64 or 128"); }
+    int T = 32;
+    long long lblock = 1;
+    {
+        int rc = choose_tiling(cfg->tile_edges, cfg->lmk_block, L, F, &T, &lblock);
+        if (rc != GBP_OK) return rc;
+    }
     if (cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) {
         if (T == 128) { return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
         if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8) g->cam_w = CAM_MF;
@@ -499,51 +622,20 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         g->cam_w = CAM_MF;
     }
     g->T = T;
-    long long lblock = cfg->lmk_block;
-    if (lblock <= 0) lblock = ((long long)L * LMK_B * 8 <= (24LL << 20)) ? std::max(L, 1) : 262144;
-    const long long nb = L > 0 ? (L + lblock - 1) / lblock : 1;
-
-    // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130)
-    std::vector<long long> cam_start((size_t)C + 1, 0);
-    for (int64_t i = 0; i < F; ++i) cam_start[cam_id[i] + 1]++;
-    for (int c = 0; c < C; ++c) cam_start[c + 1] += cam_start[c];
-    g->h_file_of_factor.assign((size_t)F, 0);
+    GraphPlan plan;
     {
-        std::vector<long long> pos(cam_start.begin(), cam_start.end() - 1);
-        for (int64_t i = 0; i < F; ++i) g->h_file_of_factor[(size_t)pos[cam_id[i]]++] = (int)i;
+        int rc = plan_graph(T, lblock, C, L, F, cam_id, lmk_id, z, &plan);
+        if (rc != GBP_OK) return rc;
     }
-    g->h_adj.assign((size_t)F * 2, 0);
-    for (int64_t f = 0; f < F; ++f) {
-        const int i = g->h_file_of_factor[(size_t)f];
-        g->h_adj[2 * f] = cam_id[i];
-        g->h_adj[2 * f + 1] = lmk_id[i];
-    }
-    // storage order: (landmark block, camera) runs, factor order inside a run
-    const size_t nkeys = (size_t)nb * (size_t)std::max(C, 1);
-    std::vector<long long> run_start(nkeys + 1, 0);
-    auto key_of = [&](int64_t f) { return (size_t)(g->h_adj[2 * f + 1] / lblock) * (size_t)C + (size_t)g->h_adj[2 * f]; };
-    for (int64_t f = 0; f < F; ++f) run_start[key_of(f) + 1]++;
-    // tiles per run
-    std::vector<Tile> tiles;
-    std::vector<long long> run_slot(nkeys, 0);
-    {
-        long long tcount = 0;
-        for (size_t k = 0; k < nkeys; ++k) {
-            const long long cnt = run_start[k + 1];
-            run_slot[k] = tcount * T;
-            long long left = cnt;
-            while (left > 0) {
-                Tile t;
-                t.cam = (int)(k % (size_t)std::max(C, 1));
-                t.count = (int)std::min<long long>(left, T);
-                tiles.push_back(t);
-                left -= t.count;
-                ++tcount;
-            }
-        }
-    }
+    const std::vector<Tile>& tiles = plan.tiles;
     g->n_tiles = (int)tiles.size();
-    g->n_slots = (long long)tiles.size() * T;
+    g->n_slots = plan.n_slots();
+    g->h_file_of_factor = std::move(plan.file_of_factor);
+    g->h_adj = std::move(plan.adj);
+    g->h_slot_of_factor = std::move(plan.slot_of_factor);
+    const std::vector<int>&h_lmk_idx = plan.lmk_idx, &h_lmk_ptr = plan.lmk_ptr, &h_lmk_slots = plan.lmk_slots,
+                          &h_cam_tile_ptr = plan.cam_tile_ptr, &h_cam_tiles = plan.cam_tiles;
+    const std::vector<double>& h_z = plan.z;
     {   // experiment switch (round 2 decides the default): early-start dependencies between the kernels of an iteration
         const char* v = getenv("GBP_PDL");
         g->pdl = v && atoi(v) != 0 && g->n_tiles <= 8192 && cfg->kernel_variant == 0;
@@ -554,40 +646,6 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         if (g->auto_large) g->cam_w = CAM_MF;
         const char* d = getenv("GBP_PF_DIST");
         g->pf_dist = d ? std::max(0, atoi(d)) : (g->auto_large ? 38400 / T : 0);
-    }
-    if (g->n_slots >= (1LL << 31)) { return fail(GBP_ERR_INVALID, "graph too large for int32 slots"); }
-    g->h_slot_of_factor.assign((size_t)F, 0);
-    {
-        std::vector<long long> pos(run_slot);
-        for (int64_t f = 0; f < F; ++f) g->h_slot_of_factor[(size_t)f] = (int)pos[key_of(f)]++;
-        // runs are contiguous in slots except for the padding of their last tile, which lies at
-        // the END of the run, so consecutive positions are correct.
-    }
-    // slot-ordered inputs
-    std::vector<int> h_lmk_idx((size_t)g->n_slots, 0);
-    std::vector<double> h_z((size_t)g->n_slots * 2, 0.0);
-    for (int64_t f = 0; f < F; ++f) {
-        const size_t s = (size_t)g->h_slot_of_factor[(size_t)f];
-        const int i = g->h_file_of_factor[(size_t)f];
-        h_lmk_idx[s] = g->h_adj[2 * f + 1];
-        h_z[2 * s] = z[2 * (size_t)i];
-        h_z[2 * s + 1] = z[2 * (size_t)i + 1];
-    }
-    // CSR by landmark over slots (factor order inside a landmark = adj_factors order)
-    std::vector<int> h_lmk_ptr((size_t)L + 1, 0), h_lmk_slots((size_t)F, 0);
-    for (int64_t f = 0; f < F; ++f) h_lmk_ptr[(size_t)g->h_adj[2 * f + 1] + 1]++;
-    for (int l = 0; l < L; ++l) h_lmk_ptr[l + 1] += h_lmk_ptr[l];
-    {
-        std::vector<int> pos(h_lmk_ptr.begin(), h_lmk_ptr.end() - 1);
-        for (int64_t f = 0; f < F; ++f) h_lmk_slots[(size_t)pos[g->h_adj[2 * f + 1]]++] = g->h_slot_of_factor[(size_t)f];
-    }
-    // CSR by camera over tiles
-    std::vector<int> h_cam_tile_ptr((size_t)C + 1, 0), h_cam_tiles(tiles.size(), 0);
-    for (const Tile& t : tiles) h_cam_tile_ptr[(size_t)t.cam + 1]++;
-    for (int c = 0; c < C; ++c) h_cam_tile_ptr[c + 1] += h_cam_tile_ptr[c];
-    {
-        std::vector<int> pos(h_cam_tile_ptr.begin(), h_cam_tile_ptr.end() - 1);
-        for (size_t t = 0; t < tiles.size(); ++t) h_cam_tiles[(size_t)pos[tiles[t].cam]++] = (int)t;
     }
 
     // ---------------- device allocation + upload ----------------
@@ -1201,6 +1259,54 @@ int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int dev
     if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "reprojection_eval: %s", cudaGetErrorString(e));
     return GBP_OK;
 }
+
+
+// ---- the host graph compiler on its own (no GPU needed): what gbp_ba_create lays out, for inspection and tests
+struct gbp_plan_s {
+    GraphPlan plan;
+    int C = 0, L = 0;
+    int64_t F = 0;
+};
+
+int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
+                    const int32_t* lmk_id, gbp_plan* out) {
+    if (!out) return fail(GBP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (C < 0 || L < 0 || F < 0) return fail(GBP_ERR_INVALID, "negative size");
+    if (F > 0 && (!cam_id || !lmk_id)) return fail(GBP_ERR_INVALID, "null measurement arrays");
+    try {
+        std::unique_ptr<gbp_plan_s> p(new gbp_plan_s());
+        p->C = C; p->L = L; p->F = F;
+        int T = 32;
+        long long lblock = 1;
+        int rc = choose_tiling(tile_edges, lmk_block, L, F, &T, &lblock);
+        if (rc == GBP_OK) rc = plan_graph(T, lblock, C, L, F, cam_id, lmk_id, nullptr, &p->plan);
+        if (rc != GBP_OK) return rc;
+        *out = p.release();
+        return GBP_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(GBP_ERR_INVALID, "out of host memory while compiling the graph");
+    }
+}
+
+int gbp_plan_sizes(gbp_plan p, int64_t out[6]) {
+    if (!p || !out) return fail(GBP_ERR_INVALID, "null argument");
+    out[0] = p->C; out[1] = p->L; out[2] = p->F; out[3] = (int64_t)p->plan.tiles.size(); out[4] = p->plan.T; out[5] = p->plan.n_slots();
+    return GBP_OK;
+}
+
+int gbp_plan_copy(gbp_plan p, int32_t* tiles, int32_t* slot_of_factor, int32_t* file_of_factor, int32_t* adj, int32_t* lmk_idx,
+                  int32_t* lmk_ptr, int32_t* lmk_slots, int32_t* cam_tile_ptr, int32_t* cam_tiles) {
+    if (!p) return fail(GBP_ERR_INVALID, "null plan");
+    const GraphPlan& g = p->plan;
+    auto cp = [](int32_t* dst, const std::vector<int>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(int)); };
+    if (tiles) for (size_t t = 0; t < g.tiles.size(); ++t) { tiles[2 * t] = g.tiles[t].cam; tiles[2 * t + 1] = g.tiles[t].count; }
+    cp(slot_of_factor, g.slot_of_factor); cp(file_of_factor, g.file_of_factor); cp(adj, g.adj); cp(lmk_idx, g.lmk_idx);
+    cp(lmk_ptr, g.lmk_ptr); cp(lmk_slots, g.lmk_slots); cp(cam_tile_ptr, g.cam_tile_ptr); cp(cam_tiles, g.cam_tiles);
+    return GBP_OK;
+}
+
+void gbp_plan_destroy(gbp_plan p) { delete p; }
 
 }  // extern "C"
 

@@ -215,3 +215,31 @@ def reprojection_eval(x, K4, device=0):
     J = np.empty((len(x), 18))
     L.check(lib.gbp_reprojection_eval(L.ptr(x), len(x), L.ptr(K4), int(device), L.ptr(h), L.ptr(J)))
     return h, J.reshape(-1, 2, 9)
+
+
+def compile_plan(cam_id, lmk_id, n_keyframes, n_landmarks, tile_edges=0, lmk_block=0):
+    """The engine's storage order for a measurement list, from the native host graph compiler (`gbp_plan_*`; pure host
+    code, no GPU needed): dict with T, tiles [(keyframe, count)], slot_of_factor, file_of_factor, adj, lmk_idx (per slot),
+    lmk_ptr / lmk_slots (CSR by landmark over slots), cam_tile_ptr / cam_tiles (CSR by keyframe over tiles)."""
+    lib = L.load()
+    cam_id = np.ascontiguousarray(cam_id, dtype=np.int32)
+    lmk_id = np.ascontiguousarray(lmk_id, dtype=np.int32)
+    if len(cam_id) != len(lmk_id):
+        raise ValueError("cam_id and lmk_id must have one entry per measurement")
+    p = C.c_void_p()
+    L.check(lib.gbp_plan_create(int(tile_edges), int(lmk_block), int(n_keyframes), int(n_landmarks), len(cam_id),
+                                L.ptr(cam_id), L.ptr(lmk_id), C.byref(p)))
+    try:
+        sizes = (C.c_int64 * 6)()
+        L.check(lib.gbp_plan_sizes(p, sizes))
+        nc, nl, nf, n_tiles, T, n_slots = [int(v) for v in sizes]
+        out = {"T": T, "n_tiles": n_tiles, "n_slots": n_slots,
+               "tiles": np.zeros((n_tiles, 2), np.int32), "slot_of_factor": np.zeros(nf, np.int32),
+               "file_of_factor": np.zeros(nf, np.int32), "adj": np.zeros((nf, 2), np.int32), "lmk_idx": np.zeros(n_slots, np.int32),
+               "lmk_ptr": np.zeros(nl + 1, np.int32), "lmk_slots": np.zeros(nf, np.int32),
+               "cam_tile_ptr": np.zeros(nc + 1, np.int32), "cam_tiles": np.zeros(n_tiles, np.int32)}
+        L.check(lib.gbp_plan_copy(p, *[L.ptr(out[k]) for k in ("tiles", "slot_of_factor", "file_of_factor", "adj", "lmk_idx",
+                                                              "lmk_ptr", "lmk_slots", "cam_tile_ptr", "cam_tiles")]))
+        return out
+    finally:
+        lib.gbp_plan_destroy(p)

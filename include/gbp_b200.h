@@ -123,6 +123,19 @@ int gbp_ba_reset(gbp_handle h);
 /* Sizes: C, L, F, number of edge tiles, edges per tile, padded edge slots. */
 int gbp_ba_sizes(gbp_handle h, int64_t out[6]);
 
+/* The host graph compiler on its own (pure host code, works without a GPU): the storage order gbp_ba_create builds
+ * from a measurement list -- factor order = stable sort by camera (gbp/gbp_ba.py:128-143), tiles of <= T edges of ONE
+ * keyframe sorted by (landmark block, keyframe), CSR by landmark over slots, CSR by keyframe over tiles.
+ * gbp_plan_sizes: C, L, F, tiles, edges per tile, slots.  gbp_plan_copy: any output may be NULL; tiles = (keyframe, count)
+ * pairs; adj = (keyframe, landmark) per factor; lmk_idx per slot (0 in padding slots). */
+typedef struct gbp_plan_s* gbp_plan;
+int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
+                    const int32_t* lmk_id, gbp_plan* out);
+int gbp_plan_sizes(gbp_plan p, int64_t out[6]);
+int gbp_plan_copy(gbp_plan p, int32_t* tiles, int32_t* slot_of_factor, int32_t* file_of_factor, int32_t* adj, int32_t* lmk_idx,
+                  int32_t* lmk_ptr, int32_t* lmk_slots, int32_t* cam_tile_ptr, int32_t* cam_tiles);
+void gbp_plan_destroy(gbp_plan p);
+
 /* Engine layout chosen for this graph (no reference counterpart; used by bench.py to count the bytes a sweep moves):
  * out[0] doubles per stored factor->keyframe message (27 full, 18 factored), out[1] L2 prefetch distance in tiles,
  * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice), out[3] programmatic launches. */

@@ -1,0 +1,95 @@
+"""The native host graph compiler (gbp_plan_*: the storage order gbp_ba_create lays out), checked on CPU against an
+independent NumPy statement of its rules.  The reference builds its factor list with an O(C F) scan
+(gbp/gbp_ba.py:128-143); the order that scan produces -- camera-major, file order inside a camera -- is the factor
+order here, everything else (tiles, landmark blocks, CSR tables) is engine layout with no reference counterpart."""
+import numpy as np
+import pytest
+
+from conftest import golden_problem, load_golden
+
+
+def _plan(cam, lmk, C, L, **kw):
+    from gbp_b200.engine import compile_plan
+    return compile_plan(cam, lmk, C, L, **kw)
+
+
+def _check(plan, cam, lmk, C, L, lblock):
+    T, tiles, F = plan["T"], plan["tiles"], len(cam)
+    order = np.argsort(cam, kind="stable")
+    # factor order = the reference's: stable sort of the measurement list by camera
+    assert np.array_equal(plan["file_of_factor"], order)
+    assert np.array_equal(plan["adj"][:, 0], cam[order]) and np.array_equal(plan["adj"][:, 1], lmk[order])
+    fcam, flmk = cam[order], lmk[order]
+    # slots: injective, inside the tile range, padding slots unmapped
+    sl = plan["slot_of_factor"]
+    assert len(np.unique(sl)) == F and (sl >= 0).all() and (sl < plan["n_slots"]).all() and plan["n_slots"] == len(tiles) * T
+    t_of, pos = sl // T, sl % T
+    assert (pos < tiles[t_of, 1]).all()                              # inside the valid part of its tile
+    assert np.array_equal(np.bincount(t_of, minlength=len(tiles)), tiles[:, 1]) and (tiles[:, 1] >= 1).all() and (tiles[:, 1] <= T).all()
+    assert np.array_equal(tiles[t_of, 0], fcam)                      # every tile holds edges of ONE keyframe
+    # tiles are sorted by (landmark block, keyframe); inside a run the factor order is kept and only the last tile is ragged
+    key = (flmk // lblock).astype(np.int64) * max(C, 1) + fcam
+    tile_key = np.full(len(tiles), -1, np.int64)
+    tile_key[t_of] = key
+    assert (np.diff(tile_key) >= 0).all()
+    assert np.array_equal(np.argsort(key, kind="stable"), np.argsort(sl))      # storage order = stable sort by run key
+    for k in np.unique(tile_key):
+        cnt = tiles[tile_key == k, 1]
+        assert (cnt[:-1] == T).all()
+    # per-slot landmark index, zero in padding
+    idx = np.zeros(plan["n_slots"], np.int32)
+    idx[sl] = flmk
+    assert np.array_equal(plan["lmk_idx"], idx)
+    # CSR by landmark over slots, factor order inside a landmark (= adj_factors order of the reference)
+    assert np.array_equal(np.diff(plan["lmk_ptr"]), np.bincount(flmk, minlength=L))
+    lorder = np.argsort(flmk, kind="stable")
+    assert np.array_equal(plan["lmk_slots"], sl[lorder])
+    # CSR by keyframe over tiles, tile order inside a keyframe
+    assert np.array_equal(np.diff(plan["cam_tile_ptr"]), np.bincount(tiles[:, 0], minlength=C))
+    assert np.array_equal(plan["cam_tiles"], np.argsort(tiles[:, 0], kind="stable"))
+
+
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk"])
+@pytest.mark.parametrize("tile,block", [(0, 0), (32, 100), (64, 0), (128, 64)])
+def test_plan_of_the_reference_problems(built_library, name, tile, block):
+    P = golden_problem(load_golden(name))
+    plan = _plan(P.cam_id, P.lmk_id, P.n_keyframes, P.n_points, tile_edges=tile, lmk_block=block)
+    assert plan["T"] == (tile or 32)                                   # small graphs: 32-edge tiles
+    _check(plan, np.asarray(P.cam_id), np.asarray(P.lmk_id), P.n_keyframes, P.n_points, block or max(P.n_points, 1))
+
+
+def test_plan_shuffled_file_order_and_isolated_variables(built_library):
+    """Measurements in random file order, keyframes and landmarks without any measurement, a landmark seen 70 times."""
+    rng = np.random.default_rng(3)
+    C, L, F = 7, 50, 400
+    cam = rng.integers(0, C - 2, F).astype(np.int32)          # keyframes 5, 6 never observed
+    lmk = rng.integers(0, L - 5, F).astype(np.int32)          # landmarks 45.. never observed
+    lmk[:70] = 3
+    plan = _plan(cam, lmk, C, L, tile_edges=32, lmk_block=16)
+    _check(plan, cam, lmk, C, L, 16)
+    assert plan["cam_tile_ptr"][5] == plan["cam_tile_ptr"][7] and plan["lmk_ptr"][45] == plan["lmk_ptr"][50]
+
+
+def test_plan_large_graph_auto_tiling(built_library):
+    """Automatic choices: 64-edge tiles from 56832 factors on; landmark blocks of 262144 once the belief rows exceed
+    24 MB (the synthetic 1 M-landmark graph is cut into 4 blocks)."""
+    from gbp_b200.synthetic import make_synthetic
+    prob = make_synthetic(50, 300_000, 4, seed=2)
+    plan = _plan(prob.cam_id, prob.lmk_id, prob.n_keyframes, prob.n_points)
+    assert plan["T"] == 64
+    _check(plan, np.asarray(prob.cam_id), np.asarray(prob.lmk_id), prob.n_keyframes, prob.n_points, 262144)
+    assert len(np.unique(np.asarray(prob.lmk_id) // 262144)) == 2
+    waste = plan["n_slots"] / len(prob.cam_id) - 1.0
+    assert waste < 0.05                                                 # padding slots: < 5 % on this graph
+
+
+def test_plan_errors_and_empty(built_library):
+    from gbp_b200 import _lib as L
+    with pytest.raises(L.GbpError, match="landmark id"):
+        _plan(np.array([0, 1], np.int32), np.array([0, 9], np.int32), 2, 3)
+    with pytest.raises(L.GbpError, match="camera id"):
+        _plan(np.array([0, -1], np.int32), np.array([0, 1], np.int32), 2, 3)
+    with pytest.raises(L.GbpError, match="tile_edges"):
+        _plan(np.array([0], np.int32), np.array([0], np.int32), 1, 1, tile_edges=48)
+    empty = _plan(np.zeros(0, np.int32), np.zeros(0, np.int32), 2, 3)
+    assert empty["n_tiles"] == 0 and empty["n_slots"] == 0 and np.array_equal(empty["lmk_ptr"], np.zeros(4, np.int32))
