@@ -108,6 +108,10 @@ struct gbp_ba_graph {
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
+    // one-kernel iteration of small graphs (kernel_variant 11, experimental): completion counters [L + C], allocated on first use
+    int* fused_counters = nullptr;
+    bool fused_eligible = false;   // 32-edge tiles, full-form messages, at most 8192 tiles, every variable has an edge
+
     // peer-memory exchange (gbp_ba_p2p_*): own buffer, the peers' buffers as mapped here, device table of the bases
     char* xchg = nullptr;
     size_t xchg_bytes = 0;
@@ -135,6 +139,7 @@ struct gbp_ba_graph {
         tile_max.release(); cam_max.release(); cam_mu0.release(); lmk_mu0.release();
         for (int r = 0; r < (int)peer_map.size(); ++r)
             if (peer_map[r] && r != p2p_rank) cudaIpcCloseMemHandle(peer_map[r]);
+        if (fused_counters) cudaFree(fused_counters);
         if (peer_tab_dev) cudaFree(peer_tab_dev);
         if (xchg) cudaFree(xchg);
         if (arena.base) cudaFree(arena.base);
@@ -317,6 +322,27 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, bool pdl = false
     return GBP_OK;
 }
 
+// kernel_variant 11: sweep + belief update of one iteration in ONE launch (sweep_fused_kernel), small graphs only
+int launch_fused(gbp_ba_graph* g, int stages) {
+    if (!g->fused_counters) {
+        const size_t n = (size_t)g->L + (size_t)g->C;
+        CU(cudaMalloc(reinterpret_cast<void**>(&g->fused_counters), std::max<size_t>(n, 1) * sizeof(int)));
+        CU(cudaMemsetAsync(g->fused_counters, 0, std::max<size_t>(n, 1) * sizeof(int), g->stream));
+    }
+    FusedParams fp{};
+    fp.sweep = sweep_params(g, stages);
+    fp.lmk_prior = g->lmk_prior.p; fp.cam_prior = g->cam_prior.p; fp.lmk_belief_out = g->lmk_belief.p; fp.cam_belief_out = g->cam_belief.p;
+    fp.cam_partial = g->cam_partial.p; fp.cam_mu = g->cam_mu.p; fp.lmk_mu = g->lmk_mu.p; fp.lmk_ptr = g->lmk_ptr.p;
+    fp.lmk_slots = g->lmk_slots.p; fp.cam_tile_ptr = g->cam_tile_ptr.p; fp.cam_tiles = g->cam_tiles.p;
+    fp.lmk_done = g->fused_counters; fp.cam_done = g->fused_counters + g->L;
+    constexpr size_t smem = sweep_smem_bytes<32>();
+    if (g->robust) sweep_fused_kernel<true><<<g->n_tiles, 32, smem, g->stream>>>(fp);
+    else sweep_fused_kernel<false><<<g->n_tiles, 32, smem, g->stream>>>(fp);
+    g->launches++;
+    CU(cudaGetLastError());
+    return GBP_OK;
+}
+
 template <int T>
 int launch_metric_t(gbp_ba_graph* g) {
     MetricParams p{};
@@ -411,7 +437,17 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     // inside the capture the kernel sequence is exactly [sweep, beliefs] x reps, which is what the early-start
     // (programmatic) dependencies of the two kernels are written for; the first node depends on the stream normally
     const bool pdl = g->pdl && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
+    const bool fused = g->cfg.kernel_variant == 11 && g->fused_eligible && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
+    if (fused && !g->fused_counters) {     // allocate outside the capture
+        cudaStreamEndCapture(g->stream, &graph);
+        if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+        const size_t n = std::max<size_t>((size_t)g->L + (size_t)g->C, 1);
+        CU(cudaMalloc(reinterpret_cast<void**>(&g->fused_counters), n * sizeof(int)));
+        CU(cudaMemset(g->fused_counters, 0, n * sizeof(int)));
+        CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+    }
     for (int r = 0; r < reps && rc == GBP_OK; ++r) {
+        if (fused) { rc = launch_fused(g, stages); continue; }
         rc = launch_sweep(g, stages, pdl);
         if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1, 3, pdl);
     }
@@ -636,6 +672,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     const std::vector<int>&h_lmk_idx = plan.lmk_idx, &h_lmk_ptr = plan.lmk_ptr, &h_lmk_slots = plan.lmk_slots,
                           &h_cam_tile_ptr = plan.cam_tile_ptr, &h_cam_tiles = plan.cam_tiles;
     const std::vector<double>& h_z = plan.z;
+    if (cfg->kernel_variant == 11) {   // one-kernel iteration: needs an edge at every variable (its last edge finalises it)
+        bool all = T == 32 && g->n_tiles > 0 && g->n_tiles <= 8192;
+        for (int l = 0; all && l < L; ++l) all = h_lmk_ptr[l + 1] > h_lmk_ptr[l];
+        for (int c = 0; all && c < C; ++c) all = h_cam_tile_ptr[c + 1] > h_cam_tile_ptr[c];
+        g->fused_eligible = all;
+    }
     {   // experiment switch (round 2 decides the default): early-start dependencies between the kernels of an iteration
         const char* v = getenv("GBP_PDL");
         g->pdl = v && atoi(v) != 0 && g->n_tiles <= 8192 && cfg->kernel_variant == 0;
@@ -926,7 +968,8 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
     constexpr int REPS = 8;
-    const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
+    const bool fused = h->cfg.kernel_variant == 11 && h->fused_eligible;      // one launch per iteration
+    const int per_iter = fused ? 1 : (h->n_tiles > 0 ? 1 : 0) + 1;
     int left = n_iters;
     if (left >= REPS && h->n_tiles <= 8192) {   // small graphs only: there the launch gaps are a visible share of an iteration
         cudaGraphExec_t exec8;

@@ -819,6 +819,161 @@ __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restric
 }
 
 // ----------------------------------------------------------------------------------------
+// One-kernel iteration for small (L2-resident, latency-bound) graphs -- kernel_variant 11, NOT YET RUN ON HARDWARE.
+//
+// fr1desk spends 9 us per iteration in two ~4.5 us kernels whose length is set by dependent latencies, not by work.
+// This kernel appends the belief update to the sweep without a grid-wide barrier: a variable's belief may be rewritten
+// as soon as ALL of its edges have been swept -- exactly the edges that read it -- so the warp that sweeps the LAST
+// tile of a keyframe (last edge of a landmark) finalises that keyframe (landmark).  "Last" is found with one
+// atomic counter per variable (incremented after the tile's results are globally visible; reset by the finaliser for
+// the next launch).  Nobody ever waits, so there is nothing to deadlock; the Jacobi semantics of
+// synchronous_iteration (gbp/gbp.py:86-92: all messages of a sweep use the beliefs of the previous one) hold because
+// every reader of a belief row has finished before the row is rewritten.  Sums run in the same fixed orders as
+// belief_kernel<32> (CSR order per landmark, tile order per keyframe), independent of which warp does them, so the
+// result is deterministic and equal to the two-kernel path.
+//   grid = tiles, block = 32 (one warp per 32-edge tile); full-form message rows; every variable has degree >= 1.
+// ----------------------------------------------------------------------------------------
+struct FusedParams {
+    SweepParams sweep;
+    const double* lmk_prior;
+    const double* cam_prior;
+    double* lmk_belief_out;        // same arrays as sweep.lmk_belief / cam_belief, writable
+    double* cam_belief_out;
+    double* cam_partial;
+    double* cam_mu;
+    double* lmk_mu;
+    const int* lmk_ptr;
+    const int* lmk_slots;
+    const int* cam_tile_ptr;
+    const int* cam_tiles;
+    int* lmk_done;                 // [L] edges of the landmark swept so far in this launch (0 between launches)
+    int* cam_done;                 // [C] tiles of the keyframe swept so far
+};
+
+template <bool ROBUST>
+__global__ void __launch_bounds__(32, 12) sweep_fused_kernel(const FusedParams fp) {
+    constexpr int T = 32;
+    const SweepParams& p = fp.sweep;
+    extern __shared__ __align__(128) double smem[];
+    double* s_mc = smem;                 // [T][27]
+    double* s_ml = s_mc + T * CAM_M;     // [T][9]
+    double* s_lp = s_ml + T * LMK_M;     // [T][9]
+    double* s_cb = s_lp + T * 9;         // [34]
+    double* s_red = s_cb + 34;           // [27]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + CAM_M);
+
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const Tile tl = p.tiles[tile];
+    const int n = tl.count, n_even = (n + 1) & ~1;
+    const long long base = (long long)tile * T;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)n_even * (CAM_M + LMK_M + 9) * 8);
+        bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
+        bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
+        bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
+    }
+    // beliefs are rewritten inside this kernel (after their last reader): plain L2 loads, never the read-only path
+    for (int i = lane; i < CAM_B; i += T) s_cb[i] = __ldcg(p.cam_belief + (long long)tl.cam * CAM_B + i);
+    EdgeRegs r;
+    int lmk = 0;
+    if (lane < n) {
+        lmk = load_edge_scalars(p, base + lane, r);
+        const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
+#pragma unroll
+        for (int k = 0; k < LMK_B / 2; ++k) {
+            const double2 v = __ldcg(src + k);
+            r.bl[2 * k] = v.x;
+            r.bl[2 * k + 1] = v.y;
+        }
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    bool relin = false;
+    if (lane < n) relin = edge_sweep<ROBUST>(p, base + lane, r, s_cb, s_lp + lane * 9, s_mc + lane * CAM_M, s_ml + lane * LMK_M);
+    __syncwarp();
+    const unsigned any_relin = __ballot_sync(0xffffffffu, relin);
+
+    // results -> global with ordinary stores (the completion protocol below reasons in the generic proxy only)
+    if (p.stages & ST_MESSAGES) {
+        coop_copy<T>(p.msg_cam + base * CAM_M, s_mc, n * CAM_M);
+        coop_copy<T>(p.msg_lmk + base * LMK_M, s_ml, n * LMK_M);
+    }
+    if (any_relin) coop_copy<T>(p.linpoint + base * 9, s_lp, n * 9);
+    if (lane < CAM_M) {                  // per-tile keyframe sums, rows added in slot order like tile_column_sums<32>
+        double acc = 0.0;
+        for (int q = 0; q < n; ++q) acc += s_mc[q * CAM_M + lane];
+        p.tile_partial[(long long)tile * CAM_M + lane] = acc;
+    }
+    __threadfence();                     // this lane's stores are visible device-wide ...
+    __syncwarp();                        // ... before any lane of the warp announces the tile
+
+    // ---- who is last?
+    int cam_last = 0;
+    if (lane == 0) {
+        const int nt = fp.cam_tile_ptr[tl.cam + 1] - fp.cam_tile_ptr[tl.cam];
+        cam_last = (atomicAdd(fp.cam_done + tl.cam, 1) + 1 == nt) ? 1 : 0;
+        if (cam_last) fp.cam_done[tl.cam] = 0;
+    }
+    cam_last = __shfl_sync(0xffffffffu, cam_last, 0);
+    bool lmk_last = false;
+    if (lane < n) {
+        const int deg = fp.lmk_ptr[lmk + 1] - fp.lmk_ptr[lmk];
+        lmk_last = atomicAdd(fp.lmk_done + lmk, 1) + 1 == deg;
+        if (lmk_last) fp.lmk_done[lmk] = 0;
+    }
+    __threadfence();                     // what the other tiles published before their increments is visible from here on
+    unsigned todo = __ballot_sync(0xffffffffu, lmk_last);
+
+    // ---- landmarks completed by this tile: the whole warp gathers one landmark's message rows at a time
+    //      (lane j takes rows j, j + 32, ... of the CSR list; fixed shuffle tree; same order as belief_kernel<32>)
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int l = __shfl_sync(0xffffffffu, lmk, src_lane);
+        const int p0 = fp.lmk_ptr[l], p1 = fp.lmk_ptr[l + 1];
+        double acc[LMK_M];
+#pragma unroll
+        for (int k = 0; k < LMK_M; ++k) acc[k] = 0.0;
+        for (int q = p0 + lane; q < p1; q += 32) {
+            const double* row = p.msg_lmk + (long long)fp.lmk_slots[q] * LMK_M;
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += __ldcg(row + k);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += fp.lmk_prior[(long long)l * LMK_M + k];
+            double mu[3];
+            spd_solve<3>(acc + 3, acc, mu);
+            double* row = fp.lmk_belief_out + (long long)l * LMK_B;
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) row[k] = acc[k];
+            row[9] = mu[0]; row[10] = mu[1]; row[11] = mu[2];
+            double* m = fp.lmk_mu + (long long)l * 3;
+            m[0] = mu[0]; m[1] = mu[1]; m[2] = mu[2];
+        }
+    }
+    // ---- keyframe completed by this tile: fixed-order sum of its tile partials, prior, 6x6 solve
+    if (cam_last) {
+        const int c = tl.cam;
+        double acc = 0.0;
+        if (lane < CAM_M) {
+            for (int q = fp.cam_tile_ptr[c]; q < fp.cam_tile_ptr[c + 1]; ++q)
+                acc += __ldcg(p.tile_partial + (long long)fp.cam_tiles[q] * CAM_M + lane);
+            fp.cam_partial[(long long)c * CAM_M + lane] = acc;
+            acc += fp.cam_prior[(long long)c * CAM_M + lane];
+        }
+        cam_finalise_row(acc, lane, fp.cam_belief_out + (long long)c * CAM_B, fp.cam_mu + (long long)c * 6);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // Peer-memory exchange of the keyframe partial sums (multi-GPU, one process per GPU; opt-in, see gbp_ba_p2p_*).
 // Replaces [all-gather of C x 27 doubles -> cam_update_kernel] by two kernels that talk through NVLink directly:
 //   p2p_scatter_kernel        every rank writes its partial sums into slot [my rank] of EVERY rank's exchange buffer

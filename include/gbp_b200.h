@@ -63,7 +63,9 @@ typedef struct gbp_config {
                                         reads and writes keep the full eta[6] | Lambda[21] form;
                                     6 = early issue: bulk loads, scalars and the landmark gather do not wait for the tile descriptor;
                                     7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments);
-                                    10 = warp-specialised persistent ring (experiment, producer-bound: 2x slower) */
+                                    10 = warp-specialised persistent ring (experiment, producer-bound: 2x slower);
+                                    11 = one-kernel iteration for small graphs (sweep + belief update in one launch through
+                                         per-variable completion counters; gbp_ba_iterate only; NOT yet run on hardware) */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */

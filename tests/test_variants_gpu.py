@@ -110,3 +110,30 @@ def test_layout_selection():
     assert (a._eng.msg_cam_width, a._eng.sweep_variant, a._eng.prefetch_tiles) == (27, 0, 0)
     assert (b._eng.msg_cam_width, b._eng.sweep_variant) == (18, 5)
     a.close(); b.close()
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="one-kernel iteration (variant 11): not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("name", ["fr1desk", "fr1desk_vsmall_huber"])
+def test_one_kernel_iteration_equals_two_kernel_path(name):
+    """kernel_variant 11: sweep + belief update in one launch through completion counters; same fixed summation orders
+    as the two-kernel path, so the same bits; ba.py's schedule incl. the resets, 200 / 60 iterations."""
+    from gbp_b200 import _lib as L
+    from gbp_b200.ba import create_ba_graph
+    G = load_golden(name)
+    n_iters = int(G["n_iters"])
+    graphs = []
+    for variant in (0, 11):
+        g = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=variant)
+        g.generate_priors_var(50.0)
+        g.update_all_beliefs()
+        g.iterate(3, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
+        g.iterate(5, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
+        g.iterate(n_iters - 8, robustify=True, local_relin=True)
+        graphs.append(g)
+    a, b = graphs
+    assert b._eng.launch_count() < a._eng.launch_count()             # really one launch per iteration
+    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ITERS, L.F_FLAGS, L.F_ADAPTIVE_VAR):
+        assert np.array_equal(a._eng.read(f), b._eng.read(f)), f
+    key = f"s{int(G['checkpoints'].max())}"
+    assert relerr(b.get_means(), np.concatenate([G[f"{key}_cam_mu"].ravel(), G[f"{key}_lmk_mu"].ravel()])) < 1e-4
+    a.close(); b.close()
