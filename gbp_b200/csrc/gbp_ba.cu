@@ -430,22 +430,19 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     const int key = stages | (reps << 8);
     auto it = g->graphs.find(key);
     if (it != g->graphs.end()) { *out = it->second; return GBP_OK; }
-    cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
-    const long long before = g->launches;
-    int rc = GBP_OK;
     // inside the capture the kernel sequence is exactly [sweep, beliefs] x reps, which is what the early-start
     // (programmatic) dependencies of the two kernels are written for; the first node depends on the stream normally
     const bool pdl = g->pdl && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
     const bool fused = g->cfg.kernel_variant == 11 && g->fused_eligible && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
-    if (fused && !g->fused_counters) {     // allocate outside the capture
-        cudaStreamEndCapture(g->stream, &graph);
-        if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+    if (fused && !g->fused_counters) {     // completion counters of the one-kernel iteration: allocated before the capture
         const size_t n = std::max<size_t>((size_t)g->L + (size_t)g->C, 1);
         CU(cudaMalloc(reinterpret_cast<void**>(&g->fused_counters), n * sizeof(int)));
         CU(cudaMemset(g->fused_counters, 0, n * sizeof(int)));
-        CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     }
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = g->launches;
+    int rc = GBP_OK;
     for (int r = 0; r < reps && rc == GBP_OK; ++r) {
         if (fused) { rc = launch_fused(g, stages); continue; }
         rc = launch_sweep(g, stages, pdl);
