@@ -122,6 +122,7 @@ struct gbp_ba_graph {
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
     Arena arena;
+    bool arena_pooled = false;   // arena from the stream-ordered pool (GBP_POOL_ALLOC=1)
     cudaEvent_t snap_event = nullptr;
     // fused [iteration + metrics + copies to pinned host buffers] graphs, keyed by stages; valid for snap_ptrs
     std::map<int, cudaGraphExec_t> snap_graphs;
@@ -142,7 +143,10 @@ struct gbp_ba_graph {
         if (fused_counters) cudaFree(fused_counters);
         if (peer_tab_dev) cudaFree(peer_tab_dev);
         if (xchg) cudaFree(xchg);
-        if (arena.base) cudaFree(arena.base);
+        if (arena.base) {
+            if (arena_pooled) cudaFreeAsync(arena.base, stream);   // before the stream is destroyed below
+            else cudaFree(arena.base);
+        }
         if (snap_event) cudaEventDestroy(snap_event);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -710,7 +714,20 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
 #undef ALLOC
         if (pass == 0) {
             A.size = A.used;
-            if ((e = cudaMalloc(reinterpret_cast<void**>(&A.base), A.size)) != cudaSuccess) return bail(e, "cudaMalloc arena");
+            // GBP_POOL_ALLOC=1 (experiment for round 2): the arena comes from the device's stream-ordered memory pool with
+            // an unlimited release threshold, so that building graph after graph stops paying cudaMalloc / cudaFree
+            // (single create calls of 5-55 ms were seen in the end-to-end bench)
+            const char* pa = getenv("GBP_POOL_ALLOC");
+            g->arena_pooled = pa && atoi(pa) != 0;
+            if (g->arena_pooled) {
+                cudaMemPool_t pool;
+                unsigned long long keep = ~0ULL;
+                if ((e = cudaDeviceGetDefaultMemPool(&pool, device)) != cudaSuccess) return bail(e, "cudaDeviceGetDefaultMemPool");
+                if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return bail(e, "cudaMemPoolSetAttribute");
+                if ((e = cudaMallocAsync(reinterpret_cast<void**>(&A.base), A.size, g->stream)) != cudaSuccess) return bail(e, "cudaMallocAsync arena");
+            } else if ((e = cudaMalloc(reinterpret_cast<void**>(&A.base), A.size)) != cudaSuccess) {
+                return bail(e, "cudaMalloc arena");
+            }
         }
     }
 #define UP(buf, vec) if (!(vec).empty() && (e = cudaMemcpyAsync(g->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload " #buf)
