@@ -43,6 +43,68 @@ def test_stdout_carries_only_the_json_line():
     assert res.stdout == '{"ok": 1}\n' and "NCCL version" in res.stderr and "python-level noise" in res.stderr
 
 
+def test_roofline_entry_counts_both_byte_figures():
+    """`achieved` = SURVEY 8(d) bytes / launch time (the contract); the factored layout's own bytes are reported beside it."""
+    sys.path.insert(0, ROOT)
+    import bench
+    F, L, C = 10_000_000, 1_000_000, 1000
+    _, survey = bench.b_alg(F, L, C)
+    _, moved = bench.b_alg(F, L, C, 18)
+    assert survey == 696 * F + 96 * L + 264 * C and moved == 552 * F + 96 * L + 264 * C
+    r = bench.roofline_entry("w", 1.0, survey, moved, 6547.8, 5_599_662_000, 18)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6547.8
+    assert abs(r["achieved"] - survey / 1e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6547.8) < 1e-12
+    assert abs(r["achieved_moved"] - moved / 1e-3 / 1e9) < 1e-6 and r["frac_moved"] < r["frac"]
+    assert r["traffic"] == 5_599_662_000 and r["ms_per_launch"] == 1.0 and "552" in r["bytes_note"]
+    full = bench.roofline_entry("w", 1.2, survey, survey, 6547.8, None, 27)
+    assert full["achieved"] == full["achieved_moved"] and full["traffic"] is None
+    json.dumps(r)
+
+
+def test_synthetic_section_builds_its_json_with_a_stub_engine(monkeypatch):
+    """bench_synthetic's bookkeeping (byte counts, roofline object, JSON-serialisable output) with the GPU engine, torch
+    and the generator replaced by stubs: a typo there would cost the round its bench line."""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    import gbp_b200.dist as gdist
+    import gbp_b200.synthetic as gsyn
+
+    class Ev:
+        def __init__(self, enable_timing=True): pass
+        def record(self): pass
+        def elapsed_time(self, other): return 24.0
+
+    torch = types.SimpleNamespace(cuda=types.SimpleNamespace(Event=Ev, current_stream=lambda: None, synchronize=lambda: None))
+
+    class Eng:
+        F, L, C, n_tiles, tile_edges = 10_000_000, 1_000_000, 1000, 158239, 64
+        msg_cam_width, sweep_variant, prefetch_tiles = 18, 7, 600
+        def launch_count(self): return 0
+        def time_iterations(self, k, r, l, per_kernel=False): return 1.2 * k, 1.0 * k
+
+    class PG:
+        p2p = False
+        def __init__(self, *a, **kw): self.engine = Eng()
+        def generate_priors_var(self, w): pass
+        def update_all_beliefs(self): pass
+        def capture(self, **kw): return False
+        def synchronous_iteration(self, **kw): pass
+        def metrics(self): return 2.3, 8.5e6, 0
+        def close(self): pass
+
+    monkeypatch.setattr(gdist, "PartitionedBAGraph", PG)
+    monkeypatch.setattr(gsyn, "make_synthetic", lambda c, l, o, seed=0: types.SimpleNamespace(n_edges=10_000_000, n_points=1_000_000, n_keyframes=1000))
+    args = types.SimpleNamespace(synth_cams=1000, synth_lmks=1_000_000, p2p=False, no_capture=False, synth_iters=20, warmup=3, synth_sustained=200)
+    synth, roof = bench.bench_synthetic(args, torch, None, 0, 1, 0, 1, 6547.8, lambda: None, lambda x: x)
+    json.dumps({"synthetic": synth, "roofline": roof})
+    assert abs(synth["ms_per_iteration"] - 1.2) < 1e-9 and synth["layout"]["msg_cam_doubles"] == 18 and synth["exchange"] is None
+    assert abs(roof["ms_per_launch"] - 1.0) < 1e-12 and roof["frac"] > 1.0 > roof["frac_moved"] > 0.8
+    assert roof["traffic"] == json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sweep_kernel/synthetic_1000_1000000_10000000"]["bytes"]
+    synth2, roof2 = bench.bench_synthetic(args, torch, None, 0, 2, 0, 1, 6547.8, lambda: None, lambda x: x)
+    assert roof2 is None and "NCCL" in synth2["exchange"] and "2 GPUs" in synth2["workload"]
+
+
 def test_build_entry_point():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
