@@ -218,7 +218,7 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
         // auto_large (kernel_variant 0, more than 8192 tiles) = 7 + far-ahead L2 prefetch: the default for HBM-bound graphs
         // (10 M-factor graph, same box: 1.257 ms per launch for the r1d kernel with early issue, 0.995 ms for this one);
         // 5 factored keyframe messages (18-double rows; T <= 64 checked at creation); 6 full rows + early issue;
-        // 7 factored + early issue; 8 / 9 = 7 / 6 compiled for 7 CTAs of 64 threads per SM (146 registers)
+        // 7 factored + early issue; 8 / 9 = 7 / 6 compiled for 7 CTAs of 64 threads per SM (ptxas settles on 128 registers, 72 B of spills)
         constexpr int TP = T <= 64 ? T : 64;
         constexpr size_t fsmem = sweep_smem_bytes<TP, true>();
         constexpr size_t esmem = sweep_smem_bytes<TP, false>();
