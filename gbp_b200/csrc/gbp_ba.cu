@@ -214,6 +214,15 @@ int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
         CU(cudaGetLastError());
         return GBP_OK;
     }
+    if (g->cfg.kernel_variant == 12) {   // 7 + keyframe sums in registers (shuffle reduce-scatter, no full-form rows in shared memory)
+        constexpr int TP = T <= 64 ? T : 64;
+        constexpr size_t rsmem = sweep_smem_bytes<TP, true, true>();
+        if (g->robust) sweep_kernel<TP, true, true, 0, false, true, true, true><<<g->n_tiles, TP, rsmem, g->stream>>>(p);
+        else sweep_kernel<TP, false, true, 0, false, true, true, true><<<g->n_tiles, TP, rsmem, g->stream>>>(p);
+        g->launches++;
+        CU(cudaGetLastError());
+        return GBP_OK;
+    }
     if (g->auto_large || (g->cfg.kernel_variant >= 5 && g->cfg.kernel_variant <= 9)) {
         // auto_large (kernel_variant 0, more than 8192 tiles) = 7 + far-ahead L2 prefetch: the default for HBM-bound graphs
         // (10 M-factor graph, same box: 1.257 ms per launch for the r1d kernel with early issue, 0.995 ms for this one);
@@ -649,9 +658,9 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         int rc = choose_tiling(cfg->tile_edges, cfg->lmk_block, L, F, &T, &lblock);
         if (rc != GBP_OK) return rc;
     }
-    if (cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) {
-        if (T == 128) { return fail(GBP_ERR_INVALID, "kernel_variants 5-9 need tile_edges 32 or 64"); }
-        if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8) g->cam_w = CAM_MF;
+    if ((cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) || cfg->kernel_variant == 12) {
+        if (T == 128) { return fail(GBP_ERR_INVALID, "kernel_variants 5-9 and 12 need tile_edges 32 or 64"); }
+        if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8 || cfg->kernel_variant == 12) g->cam_w = CAM_MF;
     }
     if (cfg->kernel_variant == 10) {   // the ring kernel works on 32-edge tiles (one consumer warp each), factored messages
         if (cfg->tile_edges != 0 && cfg->tile_edges != RING_T) { return fail(GBP_ERR_INVALID, "kernel_variant 10 needs tile_edges 0 or 32"); }
@@ -688,7 +697,7 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         g->auto_large = cfg->kernel_variant == 0 && g->n_tiles > 8192 && T <= 64;
         if (g->auto_large) g->cam_w = CAM_MF;
         const char* d = getenv("GBP_PF_DIST");
-        g->pf_dist = d ? std::max(0, atoi(d)) : (g->auto_large ? 38400 / T : 0);
+        g->pf_dist = d ? std::max(0, atoi(d)) : ((g->auto_large || (cfg->kernel_variant == 12 && g->n_tiles > 8192)) ? 38400 / T : 0);
     }
 
     // ---------------- device allocation + upload ----------------

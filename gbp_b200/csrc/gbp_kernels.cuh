@@ -140,6 +140,26 @@ __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e
     gather_lmk_belief<HINTS>(p, lmk, r);
 }
 
+// Sum of v[0..26] over the 32 lanes of a warp; lane c (< 27) returns column c.  Reduce-scatter butterfly: at distance
+// 16, 8, 4, 2, 1 a lane keeps the half of its columns selected by the corresponding bit of its lane id and adds the
+// partner's copy of that half: 31 doubles exchanged instead of 27 x 5.  Fixed tree => deterministic.
+__device__ __forceinline__ double warp_column_sums27(const double* full, int lane) {
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < CAM_M ? full[k] : 0.0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+            const double keep = up ? v[w + j] : v[j];
+            const double give = up ? v[j] : v[w + j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, give, w);
+        }
+    }
+    return v[0];
+}
+
 // column sums of the tile's (new) messages to its keyframe -> tile_partial[tile][27]
 template <int T>
 __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile, int n, const double* s_mc, double* s_red) {
@@ -184,8 +204,12 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
 // (padding slots hold landmark 0, zero rows, iters = -1), so the bulk loads fetch all T rows and every thread loads its
 // scalars and gathers its landmark row unconditionally at once; the descriptor (count, keyframe) arrives in parallel
 // and is only needed for the keyframe row and the stores.  Dependent DRAM round trips before the edge code: 3 -> 2.
-template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false, bool EARLY = false>
+// REGSUM = true (kernel_variant 12, with FACT): the keyframe-side sums of the tile are formed in registers by the shuffle
+// reduce-scatter above instead of through full-form rows in shared memory (no s_full: 13.8 KB less per 64-edge CTA, 27
+// shared stores per thread and one CTA barrier less); the warps' column sums meet in s_red.
+template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false, bool EARLY = false, bool REGSUM = false>
 __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T) sweep_kernel(const SweepParams p) {
+    static_assert(!REGSUM || FACT, "register column sums are written for the factored layout");
     extern __shared__ __align__(128) double smem[];
     constexpr int CW = FACT ? CAM_MF : CAM_M;
     double* s_mc = smem;                 // [T][27]  (or [T][18] factored)
@@ -268,9 +292,18 @@ __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T
     mbar_wait(bar, 0);        // bulk loads landed
 
     bool relin = false;
-    if (tid < n)
+    double full[REGSUM ? CAM_M : 1];
+    if (tid < n) {
         relin = edge_sweep<ROBUST, FACT>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
-                                         FACT ? s_full + tid * CAM_M : nullptr);
+                                         REGSUM ? full : (FACT ? s_full + tid * CAM_M : nullptr));
+    } else if (REGSUM) {
+#pragma unroll
+        for (int j = 0; j < (REGSUM ? CAM_M : 1); ++j) full[j] = 0.0;
+    }
+    if (REGSUM && (p.stages & ST_BELIEFS)) {     // whole warps take part (tiles are padded to T threads)
+        const double col = warp_column_sums27(full, tid & 31);
+        if ((tid & 31) < CAM_M) s_red[(tid >> 5) * CAM_M + (tid & 31)] = col;
+    }
     fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
@@ -293,7 +326,16 @@ __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T
         }
         bulk_commit();
     }
-    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, FACT ? s_full : s_mc, s_red);
+    if (REGSUM) {
+        if ((p.stages & ST_BELIEFS) && tid < CAM_M) {        // s_red was completed before the barrier above
+            double acc = s_red[tid];
+#pragma unroll
+            for (int g = 1; g < T / 32; ++g) acc += s_red[g * CAM_M + tid];
+            p.tile_partial[(long long)tile * CAM_M + tid] = acc;
+        }
+    } else if (p.stages & ST_BELIEFS) {
+        tile_column_sums<T>(p, tile, n, FACT ? s_full : s_mc, s_red);
+    }
     if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
 }
 
@@ -443,26 +485,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 // arrive on `bar` once every cp.async issued so far by this thread has landed (counted in the barrier's expected arrivals)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Sum of v[0..26] over the 32 lanes of a warp; lane c (< 27) returns column c.  Reduce-scatter butterfly: at distance
-// 16, 8, 4, 2, 1 a lane keeps the half of its columns selected by the corresponding bit of its lane id and adds the
-// partner's copy of that half: 31 doubles exchanged instead of 27 x 5.  Fixed tree => deterministic.
-__device__ __forceinline__ double warp_column_sums27(const double* full, int lane) {
-    double v[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = k < CAM_M ? full[k] : 0.0;
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const bool up = (lane & w) != 0;
-#pragma unroll
-        for (int j = 0; j < w; ++j) {
-            const double keep = up ? v[w + j] : v[j];
-            const double give = up ? v[j] : v[w + j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, give, w);
-        }
-    }
-    return v[0];
 }
 
 template <bool ROBUST>
@@ -653,9 +675,9 @@ __global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
     if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
 }
 
-template <int T, bool FACT = false>
+template <int T, bool FACT = false, bool REGSUM = false>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(double) * (size_t)(T * ((FACT ? CAM_MF + CAM_M : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
+    return sizeof(double) * (size_t)(T * ((FACT ? (REGSUM ? CAM_MF : CAM_MF + CAM_M) : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
 }
 
 // ----------------------------------------------------------------------------------------

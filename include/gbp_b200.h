@@ -65,7 +65,9 @@ typedef struct gbp_config {
                                     7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments);
                                     10 = warp-specialised persistent ring (experiment, producer-bound: 2x slower);
                                     11 = one-kernel iteration for small graphs (sweep + belief update in one launch through
-                                         per-variable completion counters; gbp_ba_iterate only; NOT yet run on hardware) */
+                                         per-variable completion counters; gbp_ba_iterate only; NOT yet run on hardware);
+                                    12 = 7 with the per-tile keyframe sums formed in registers (shuffle reduce-scatter) instead of through
+                                         full-form rows in shared memory, L2 prefetch on large graphs; NOT yet run on hardware */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */

@@ -9,6 +9,7 @@ case "$1" in
 one)
   echo "== one-kernel iteration (variant 11) + ring kernel: parity"; GBP_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_variants_gpu.py -q -x --no-header -p no:cacheprovider > gpurun_out/r2_exp_tests.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/r2_exp_tests.log
   echo "== fr1desk A/B: default vs variant 11"; timeout 60 python scripts/ab_variants.py --variants 11 --skip-synthetic --reps 9 > gpurun_out/r2_ab_v11.log 2>&1; echo "rc=$?"; cut -c1-400 gpurun_out/r2_ab_v11.log
+  echo "== 10 M-factor graph: default (7 + prefetch) vs 12 (register column sums)"; timeout 120 python scripts/ab_variants.py --skip-fr1desk --variants 12 > gpurun_out/r2_ab_v12.log 2>&1; echo "rc=$?"; cut -c1-500 gpurun_out/r2_ab_v12.log
   echo "== end-to-end with / without the pooled arena"; for p in 0 1; do GBP_POOL_ALLOC=$p GBP_BENCH_DEBUG=1 timeout 120 python bench.py --no-synthetic --no-cpu-baseline --steps 10 > gpurun_out/r2_bench_pool$p.json 2> gpurun_out/r2_bench_pool$p.err; echo "pool=$p rc=$?"; python - <<PY
 import json
 d = json.load(open("gpurun_out/r2_bench_pool$p.json"))

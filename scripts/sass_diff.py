@@ -38,13 +38,21 @@ def main():
         lib = os.path.join(tmp, "lib.so")
         subprocess.run([build.find_nvcc()] + build.NVCC_FLAGS + ["-o", lib, os.path.join(tmp, "gbp_b200", "csrc", "gbp_ba.cu")], check=True)
         old = kernels(lib)
-    changed = sorted(k for k in old if k in cur and old[k] != cur[k])
-    gone = sorted(k for k in old if k not in cur)
-    new = sorted(k for k in cur if k not in old)
-    print(f"{len(old)} kernels at {commit}: {len(old) - len(changed) - len(gone)} identical, {len(changed)} changed, {len(gone)} removed; {len(new)} new")
-    for tag, names in (("CHANGED", changed), ("REMOVED", gone), ("NEW", new)):
-        for k in names:
-            print(tag, k)
+    # a new template parameter renames every instantiation: match by code, not by name
+    bodies = set(cur.values())
+    changed = sorted(k for k in old if k in cur and old[k] != cur[k] and old[k] not in bodies)
+    gone = sorted(k for k in old if k not in cur and old[k] not in bodies)
+    renamed = sorted(k for k in old if k not in cur and old[k] in bodies)
+    old_bodies = set(old.values())
+    new = sorted(k for k in cur if cur[k] not in old_bodies)
+    print(f"{len(old)} kernels at {commit}: {len(old) - len(changed) - len(gone)} with identical code ({len(renamed)} of them under a new name), "
+          f"{len(changed)} changed, {len(gone)} removed; {len(new)} new")
+    try:
+        for tag, names in (("CHANGED", changed), ("REMOVED", gone), ("NEW", new)):
+            for k in names:
+                print(tag, k)
+    except BrokenPipeError:
+        pass
     sys.exit(1 if changed or gone else 0)
 
 

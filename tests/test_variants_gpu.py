@@ -48,7 +48,8 @@ def test_factored_messages_fr1desk_200_iterations():
 
 
 @pytest.mark.parametrize("variant", [5, 6, 7, 8, 9,
-                                     pytest.param(10, marks=pytest.mark.skipif(not EXPERIMENTAL, reason="ring kernel: set GBP_TEST_EXPERIMENTAL=1"))])
+                                     pytest.param(10, marks=pytest.mark.skipif(not EXPERIMENTAL, reason="ring kernel: set GBP_TEST_EXPERIMENTAL=1")),
+                                     pytest.param(12, marks=pytest.mark.skipif(not EXPERIMENTAL, reason="register column sums: not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1"))])
 def test_variants_equal_default_engine_and_round_trip(variant):
     """Same graph, default engine vs variant, 64-edge tiles with landmark blocks (ragged tiles): same state; a message
     table written by the client (full form) reads back unchanged and the sweep continues identically from it."""
