@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -92,10 +93,9 @@ struct gbp_ba_graph {
     long long n_slots = 0;
     bool robust = false;
     bool priors_set = false;
-    int cam_w = CAM_M;   // doubles per stored factor->keyframe message: 27, or 18 with the factored layout (kernel_variant 5)
-    int pf_dist = 0;     // L2 prefetch distance in tiles (auto for large graphs; GBP_PF_DIST overrides)
-    bool auto_large = false;   // kernel_variant 0 on a large graph: factored messages + early issue + L2 prefetch
-    bool pdl = false;    // programmatic dependent launch between the kernels of captured iterations (GBP_PDL=1, small graphs)
+    bool streaming = false;   // HBM-bound build of the sweep kernel: factored keyframe messages + early issue + L2 prefetch
+    int cam_w = CAM_M;   // doubles per stored factor->keyframe message: 27, or 18 with the factored layout (streaming)
+    int pf_dist = 0;     // L2 prefetch distance in tiles (streaming build only)
     long long launches = 0;
 
     // host copies (factor order)
@@ -108,10 +108,6 @@ struct gbp_ba_graph {
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
-    // one-kernel iteration of small graphs (kernel_variant 11, experimental): completion counters [L + C], allocated on first use
-    int* fused_counters = nullptr;
-    bool fused_eligible = false;   // 32-edge tiles, full-form messages, at most 8192 tiles, every variable has an edge
-
     // peer-memory exchange (gbp_ba_p2p_*): own buffer, the peers' buffers as mapped here, device table of the bases
     char* xchg = nullptr;
     size_t xchg_bytes = 0;
@@ -122,53 +118,142 @@ struct gbp_ba_graph {
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
     Arena arena;
-    bool arena_pooled = false;   // arena from the stream-ordered pool (GBP_POOL_ALLOC=1)
+    size_t upload_off = 0, upload_bytes = 0;   // the static tables of the graph: ONE contiguous region = one host->device copy
+    size_t zero_off = 0, zero_bytes = 0;       // everything gbp_ba_reset clears: ONE contiguous region = one memset
+    void* stage = nullptr;                     // page-locked staging block of that copy (from the shell cache)
+    size_t stage_bytes = 0;
     cudaEvent_t snap_event = nullptr;
     // fused [iteration + metrics + copies to pinned host buffers] graphs, keyed by stages; valid for snap_ptrs
     std::map<int, cudaGraphExec_t> snap_graphs;
     void* snap_ptr = nullptr;
     size_t snap_bytes = 0;   // metric_out .. end of lmk_belief (start of the arena)
 
-    ~gbp_ba_graph() {
+    ~gbp_ba_graph();
+};
+
+// ----------------------------------------------------------------------------------------
+// Shell cache.  What a destroyed graph leaves behind for the next one: its device arena, its page-locked staging block
+// and -- when the next graph has the SAME shape (sizes, tiling, parameters, intrinsics => the same arena layout and the
+// same kernel arguments) -- its instantiated CUDA graphs.  A client that solves problem after problem
+// (create_ba_graph -> iterate -> destroy, i.e. ba.py once per file) then pays neither cudaMalloc / cudaFree (~0.5 ms each,
+// cudaFree synchronises the device; single create calls of 5-55 ms were measured in round 1) nor cudaGraphInstantiate.
+// Bounded: at most g_cache_max_shells shells, arenas above g_cache_max_arena bytes are never kept.
+// ----------------------------------------------------------------------------------------
+namespace {
+
+struct ShapeKey {           // compared bytewise: always built by make_key (zero-filled first)
+    int device, C, L, T, n_tiles, cam_w, pf_dist, streaming, robust, resident;
+    long long F, n_slots;
+    double cfg_d[4];
+    int cfg_i[6];
+    double K[4];
+};
+
+struct Shell {
+    int device = 0;
+    char* arena = nullptr;
+    size_t arena_size = 0;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    bool has_key = false;
+    ShapeKey key;
+    std::map<int, cudaGraphExec_t> graphs, snap_graphs;
+    void* snap_ptr = nullptr;
+    void drop_graphs() {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         for (auto& kv : snap_graphs) cudaGraphExecDestroy(kv.second);
-        tiles.release(); lmk_idx.release(); iters.release(); flags.release(); slot_of_factor.release();
-        lmk_ptr.release(); lmk_slots.release(); cam_tile_ptr.release(); cam_tiles.release();
-        z.release(); linpoint.release(); msg_cam.release(); msg_lmk.release(); sigma2a.release();
-        cam_belief.release(); lmk_belief.release(); cam_prior.release(); lmk_prior.release(); cam_partial.release();
-        tile_partial.release(); tile_metric.release(); metric_out.release(); edge_max.release();
-        tile_max.release(); cam_max.release(); cam_mu0.release(); lmk_mu0.release();
-        for (int r = 0; r < (int)peer_map.size(); ++r)
-            if (peer_map[r] && r != p2p_rank) cudaIpcCloseMemHandle(peer_map[r]);
-        if (fused_counters) cudaFree(fused_counters);
-        if (peer_tab_dev) cudaFree(peer_tab_dev);
-        if (xchg) cudaFree(xchg);
-        if (arena.base) {
-            if (arena_pooled) cudaFreeAsync(arena.base, stream);   // before the stream is destroyed below
-            else cudaFree(arena.base);
-        }
-        if (snap_event) cudaEventDestroy(snap_event);
-        if (own_stream && stream) cudaStreamDestroy(stream);
+        graphs.clear();
+        snap_graphs.clear();
+        snap_ptr = nullptr;
+        has_key = false;
+    }
+    void free_all() {
+        drop_graphs();
+        if (arena) cudaFree(arena);
+        if (stage) cudaFreeHost(stage);
+        arena = nullptr;
+        stage = nullptr;
     }
 };
 
+std::mutex g_cache_mu;
+std::vector<Shell> g_shells;                 // oldest first
+int g_cache_max_shells = 4;
+size_t g_cache_max_arena = size_t(1) << 30;
+long long g_cache_stats[4] = {0, 0, 0, 0};   // creates, arena reuses, graph reuses, shells evicted
+
+ShapeKey make_key(const gbp_ba_graph* g);
+
+// Best shell for a new graph: the one of the same shape (its graphs stay valid), else the smallest arena that fits.
+bool cache_take(const ShapeKey& key, int device, size_t arena_need, Shell* out) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_stats[0]++;
+    int best = -1;
+    for (int i = 0; i < (int)g_shells.size(); ++i) {
+        const Shell& sh = g_shells[i];
+        if (sh.device != device || sh.arena_size < arena_need) continue;
+        if (sh.has_key && memcmp(&sh.key, &key, sizeof(key)) == 0) { best = i; break; }
+        if (best < 0 || sh.arena_size < g_shells[best].arena_size) best = i;
+    }
+    if (best < 0) return false;
+    *out = std::move(g_shells[best]);
+    g_shells.erase(g_shells.begin() + best);
+    if (!(out->has_key && memcmp(&out->key, &key, sizeof(key)) == 0)) out->drop_graphs();
+    g_cache_stats[1]++;
+    if (out->has_key) g_cache_stats[2]++;
+    return true;
+}
+
+void cache_put(Shell&& sh) {
+    if (!sh.arena || sh.arena_size > g_cache_max_arena || g_cache_max_shells <= 0) { sh.free_all(); return; }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_shells.push_back(std::move(sh));
+    while ((int)g_shells.size() > g_cache_max_shells) {
+        g_shells.front().free_all();
+        g_shells.erase(g_shells.begin());
+        g_cache_stats[3]++;
+    }
+}
+
+}  // namespace
+
+gbp_ba_graph::~gbp_ba_graph() {
+    for (int r = 0; r < (int)peer_map.size(); ++r)
+        if (peer_map[r] && r != p2p_rank) cudaIpcCloseMemHandle(peer_map[r]);
+    if (peer_tab_dev) cudaFree(peer_tab_dev);
+    if (xchg) cudaFree(xchg);
+    if (snap_event) cudaEventDestroy(snap_event);
+    // everything else goes back to the shell cache (the stream was synchronised by gbp_ba_destroy; a graph that dies
+    // on an error path of gbp_ba_create has nothing in flight that reads the arena after its failed call returned)
+    Shell sh;
+    sh.device = device;
+    sh.arena = arena.base; sh.arena_size = arena.size;
+    sh.stage = stage; sh.stage_bytes = stage_bytes;
+    sh.graphs = std::move(graphs); sh.snap_graphs = std::move(snap_graphs); sh.snap_ptr = snap_ptr;
+    sh.key = make_key(this);
+    sh.has_key = arena.base != nullptr;
+    if (arena.base || stage) {
+        if (stream) cudaStreamSynchronize(stream);
+        cache_put(std::move(sh));
+    } else {
+        sh.free_all();
+    }
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
 namespace {
 
-// kernel launch with the programmatic-stream-serialisation attribute (the kernel may start while its predecessor in the
-// stream is still running and synchronises with griddepcontrol.wait, see pdl_wait() in gbp_kernels.cuh)
-template <typename P>
-cudaError_t launch_pdl(void (*kernel)(const P), int grid, int block, size_t smem, cudaStream_t stream, const P& p) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, p);
+ShapeKey make_key(const gbp_ba_graph* g) {
+    ShapeKey k;
+    memset(&k, 0, sizeof(k));
+    k.device = g->device; k.C = g->C; k.L = g->L; k.T = g->T; k.n_tiles = g->n_tiles; k.cam_w = g->cam_w; k.pf_dist = g->pf_dist;
+    k.streaming = g->streaming ? 1 : 0; k.robust = g->robust ? 1 : 0; k.resident = 0;
+    k.F = g->F; k.n_slots = g->n_slots;
+    k.cfg_d[0] = g->cfg.gauss_noise_std; k.cfg_d[1] = g->cfg.eta_damping; k.cfg_d[2] = g->cfg.beta; k.cfg_d[3] = g->cfg.Nstds;
+    k.cfg_i[0] = g->cfg.num_undamped_iters; k.cfg_i[1] = g->cfg.min_linear_iters; k.cfg_i[2] = g->cfg.loss;
+    k.cfg_i[3] = g->cfg.tile_edges; k.cfg_i[4] = g->cfg.lmk_block; k.cfg_i[5] = g->cfg.kernel_variant;
+    k.K[0] = g->K.fx; k.K[1] = g->K.fy; k.K[2] = g->K.cx; k.K[3] = g->K.cy;
+    return k;
 }
 
 SweepParams sweep_params(gbp_ba_graph* g, int stages) {
@@ -185,172 +270,54 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
 }
 
 template <int T>
-int launch_sweep_t(gbp_ba_graph* g, int stages, bool pdl) {
+int launch_sweep_t(gbp_ba_graph* g, int stages) {
     const SweepParams p = sweep_params(g, stages);
-    constexpr size_t smem = sweep_smem_bytes<T>();
-    static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
-    if (pdl && g->cfg.kernel_variant == 0 && T <= 64) {   // inside captured iterations of small graphs only
-        constexpr int TP = T <= 64 ? T : 64;
-        cudaError_t e = g->robust ? launch_pdl(sweep_kernel<TP, true, true, 0, true>, g->n_tiles, TP, smem, g->stream, p)
-                                  : launch_pdl(sweep_kernel<TP, false, true, 0, true>, g->n_tiles, TP, smem, g->stream, p);
-        g->launches++;
-        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "sweep_kernel (programmatic launch): %s", cudaGetErrorString(e));
-        return GBP_OK;
-    }
-    if (g->cfg.kernel_variant == 10) {   // warp-specialised persistent ring (factored messages, 32-edge tiles)
-        static_assert(ring_smem_bytes() <= 227 * 1024, "ring must fit the opt-in shared memory of one SM");
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-        const int grid = std::min(g->n_tiles, sms);
-        const int block = 32 * (RING_CONSUMERS + 1);
-        if (g->robust) {
-            CU(cudaFuncSetAttribute(sweep_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes()));
-            sweep_ring_kernel<true><<<grid, block, ring_smem_bytes(), g->stream>>>(p);
-        } else {
-            CU(cudaFuncSetAttribute(sweep_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes()));
-            sweep_ring_kernel<false><<<grid, block, ring_smem_bytes(), g->stream>>>(p);
-        }
-        g->launches++;
-        CU(cudaGetLastError());
-        return GBP_OK;
-    }
-    if (g->cfg.kernel_variant == 12) {   // 7 + keyframe sums in registers (shuffle reduce-scatter, no full-form rows in shared memory)
-        constexpr int TP = T <= 64 ? T : 64;
-        constexpr size_t rsmem = sweep_smem_bytes<TP, true, true>();
-        if (g->robust) sweep_kernel<TP, true, true, 0, false, true, true, true><<<g->n_tiles, TP, rsmem, g->stream>>>(p);
-        else sweep_kernel<TP, false, true, 0, false, true, true, true><<<g->n_tiles, TP, rsmem, g->stream>>>(p);
-        g->launches++;
-        CU(cudaGetLastError());
-        return GBP_OK;
-    }
-    if (g->auto_large || (g->cfg.kernel_variant >= 5 && g->cfg.kernel_variant <= 9)) {
-        // auto_large (kernel_variant 0, more than 8192 tiles) = 7 + far-ahead L2 prefetch: the default for HBM-bound graphs
-        // (10 M-factor graph, same box: 1.257 ms per launch for the r1d kernel with early issue, 0.995 ms for this one);
-        // 5 factored keyframe messages (18-double rows; T <= 64 checked at creation); 6 full rows + early issue;
-        // 7 factored + early issue; 8 / 9 = 7 / 6 compiled for 7 CTAs of 64 threads per SM (ptxas settles on 128 registers, 72 B of spills)
-        constexpr int TP = T <= 64 ? T : 64;
-        constexpr size_t fsmem = sweep_smem_bytes<TP, true>();
-        constexpr size_t esmem = sweep_smem_bytes<TP, false>();
-        static_assert(fsmem <= 48 * 1024, "factored sweep tile must fit the default dynamic shared memory limit");
-#define GBP_LAUNCH_V(OCC, FACT, EARLY, SMEM)                                                                        \
-        do {                                                                                                        \
-            if (g->robust) sweep_kernel<TP, true, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);  \
-            else sweep_kernel<TP, false, true, OCC, false, FACT, EARLY><<<g->n_tiles, TP, SMEM, g->stream>>>(p);           \
-        } while (0)
-        switch (g->auto_large ? 7 : g->cfg.kernel_variant) {
-            case 5: GBP_LAUNCH_V(0, true, false, fsmem); break;
-            case 6: GBP_LAUNCH_V(0, false, true, esmem); break;
-            case 7: GBP_LAUNCH_V(0, true, true, fsmem); break;
-            case 8: GBP_LAUNCH_V(2, true, true, fsmem); break;
-            default: GBP_LAUNCH_V(2, false, true, esmem); break;
-        }
-#undef GBP_LAUNCH_V
-        g->launches++;
-        CU(cudaGetLastError());
-        return GBP_OK;
-    }
-    if (g->cfg.kernel_variant == 4 && T <= 64) {   // persistent double-buffered kernel
-        constexpr size_t psmem = sweep_persistent_smem_bytes<(T <= 64 ? T : 64)>();
-        static_assert(psmem <= 48 * 1024, "persistent sweep stages must fit the default dynamic shared memory limit");
-        int sms = 148, per_sm = 4;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device);
-        if (g->robust) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel_persistent<(T <= 64 ? T : 64), true>, T, psmem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel_persistent<(T <= 64 ? T : 64), false>, T, psmem);
-        const int grid = std::min(g->n_tiles, std::max(1, per_sm) * sms);
-        if (g->robust)
-            sweep_kernel_persistent<(T <= 64 ? T : 64), true><<<grid, T, psmem, g->stream>>>(p);
-        else
-            sweep_kernel_persistent<(T <= 64 ? T : 64), false><<<grid, T, psmem, g->stream>>>(p);
-    } else if (g->cfg.kernel_variant == 1) {   // first-version kernel (cooperative LDG/STS staging), for A/B measurements
-        if (g->robust)
-            sweep_kernel_ldg<T, true><<<g->n_tiles, T, smem, g->stream>>>(p);
-        else
-            sweep_kernel_ldg<T, false><<<g->n_tiles, T, smem, g->stream>>>(p);
-    } else if (g->cfg.kernel_variant == 3) {   // TMA + hints, compiled for 16 warps per SM (128 registers)
-        if (g->robust)
-            sweep_kernel<T, true, true, 1><<<g->n_tiles, T, smem, g->stream>>>(p);
-        else
-            sweep_kernel<T, false, true, 1><<<g->n_tiles, T, smem, g->stream>>>(p);
-    } else if (g->cfg.kernel_variant == 2) {   // TMA kernel without L2 eviction hints, for A/B measurements
-        if (g->robust)
-            sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
-        else
-            sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
-    } else if (g->robust) {
-        sweep_kernel<T, true, true><<<g->n_tiles, T, smem, g->stream>>>(p);
+    if (g->streaming) {
+        // HBM-bound graphs (more than 8192 tiles, or kernel_variant 2): factored keyframe messages, early issue, far-ahead
+        // L2 prefetch (10 M-factor graph, same box: 1.257 ms per launch for the descriptor-first full-row build, 0.995 ms for this one)
+        constexpr int TP = T <= 64 ? T : 64;      // T <= 64 checked at creation
+        constexpr size_t smem = sweep_smem_bytes<TP, true>();
+        static_assert(smem <= 48 * 1024, "factored sweep tile must fit the default dynamic shared memory limit");
+        if (g->robust) sweep_kernel<TP, true, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
+        else sweep_kernel<TP, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
     } else {
-        sweep_kernel<T, false, true><<<g->n_tiles, T, smem, g->stream>>>(p);
+        constexpr size_t smem = sweep_smem_bytes<T, false>();
+        static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
+        if (g->robust) sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+        else sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
     }
     g->launches++;
     CU(cudaGetLastError());
     return GBP_OK;
 }
 
-int launch_sweep(gbp_ba_graph* g, int stages, bool pdl = false) {
+int launch_sweep(gbp_ba_graph* g, int stages) {
     if (g->n_tiles == 0) return GBP_OK;
     switch (g->T) {
-        case 32: return launch_sweep_t<32>(g, stages, pdl);
-        case 64: return launch_sweep_t<64>(g, stages, pdl);
-        default: return launch_sweep_t<128>(g, stages, false);
+        case 32: return launch_sweep_t<32>(g, stages);
+        case 64: return launch_sweep_t<64>(g, stages);
+        default: return launch_sweep_t<128>(g, stages);
     }
 }
 
 // landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise); parts: bit0 keyframes, bit1 landmarks
-int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, bool pdl = false) {
+int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     BeliefParams p{};
-    p.pdl = pdl ? 1 : 0;
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
-    static const int lanes_override = getenv("GBP_LMK_LANES") ? atoi(getenv("GBP_LMK_LANES")) : 0;   // experiments only
     // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds
-    const int lanes = lanes_override ? lanes_override : (g->L >= 131072 ? 1 : (g->L > 8192 ? 8 : 32));
+    const int lanes = g->L >= 131072 ? 1 : (g->L > 8192 ? 8 : 32);
     const int per_cta = 128 / lanes;
     const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
-    if (pdl) {
-        cudaError_t e;
-        switch (lanes) {
-            case 1: e = launch_pdl(belief_kernel<1>, blocks, 128, 0, g->stream, p); break;
-            case 2: e = launch_pdl(belief_kernel<2>, blocks, 128, 0, g->stream, p); break;
-            case 4: e = launch_pdl(belief_kernel<4>, blocks, 128, 0, g->stream, p); break;
-            case 32: e = launch_pdl(belief_kernel<32>, blocks, 128, 0, g->stream, p); break;
-            default: e = launch_pdl(belief_kernel<8>, blocks, 128, 0, g->stream, p); break;
-        }
-        g->launches++;
-        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "belief_kernel (programmatic launch): %s", cudaGetErrorString(e));
-        return GBP_OK;
-    }
     switch (lanes) {
         case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
-        case 2: belief_kernel<2><<<blocks, 128, 0, g->stream>>>(p); break;
-        case 4: belief_kernel<4><<<blocks, 128, 0, g->stream>>>(p); break;
-        case 32: belief_kernel<32><<<blocks, 128, 0, g->stream>>>(p); break;
-        default: belief_kernel<8><<<blocks, 128, 0, g->stream>>>(p); break;
+        case 8: belief_kernel<8><<<blocks, 128, 0, g->stream>>>(p); break;
+        default: belief_kernel<32><<<blocks, 128, 0, g->stream>>>(p); break;
     }
-    g->launches++;
-    CU(cudaGetLastError());
-    return GBP_OK;
-}
-
-// kernel_variant 11: sweep + belief update of one iteration in ONE launch (sweep_fused_kernel), small graphs only
-int launch_fused(gbp_ba_graph* g, int stages) {
-    if (!g->fused_counters) {
-        const size_t n = (size_t)g->L + (size_t)g->C;
-        CU(cudaMalloc(reinterpret_cast<void**>(&g->fused_counters), std::max<size_t>(n, 1) * sizeof(int)));
-        CU(cudaMemsetAsync(g->fused_counters, 0, std::max<size_t>(n, 1) * sizeof(int), g->stream));
-    }
-    FusedParams fp{};
-    fp.sweep = sweep_params(g, stages);
-    fp.lmk_prior = g->lmk_prior.p; fp.cam_prior = g->cam_prior.p; fp.lmk_belief_out = g->lmk_belief.p; fp.cam_belief_out = g->cam_belief.p;
-    fp.cam_partial = g->cam_partial.p; fp.cam_mu = g->cam_mu.p; fp.lmk_mu = g->lmk_mu.p; fp.lmk_ptr = g->lmk_ptr.p;
-    fp.lmk_slots = g->lmk_slots.p; fp.cam_tile_ptr = g->cam_tile_ptr.p; fp.cam_tiles = g->cam_tiles.p;
-    fp.lmk_done = g->fused_counters; fp.cam_done = g->fused_counters + g->L;
-    constexpr size_t smem = sweep_smem_bytes<32>();
-    if (g->robust) sweep_fused_kernel<true><<<g->n_tiles, 32, smem, g->stream>>>(fp);
-    else sweep_fused_kernel<false><<<g->n_tiles, 32, smem, g->stream>>>(fp);
     g->launches++;
     CU(cudaGetLastError());
     return GBP_OK;
@@ -443,23 +410,13 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     const int key = stages | (reps << 8);
     auto it = g->graphs.find(key);
     if (it != g->graphs.end()) { *out = it->second; return GBP_OK; }
-    // inside the capture the kernel sequence is exactly [sweep, beliefs] x reps, which is what the early-start
-    // (programmatic) dependencies of the two kernels are written for; the first node depends on the stream normally
-    const bool pdl = g->pdl && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
-    const bool fused = g->cfg.kernel_variant == 11 && g->fused_eligible && (stages & ST_BELIEFS) && (stages & ST_MESSAGES);
-    if (fused && !g->fused_counters) {     // completion counters of the one-kernel iteration: allocated before the capture
-        const size_t n = std::max<size_t>((size_t)g->L + (size_t)g->C, 1);
-        CU(cudaMalloc(reinterpret_cast<void**>(&g->fused_counters), n * sizeof(int)));
-        CU(cudaMemset(g->fused_counters, 0, n * sizeof(int)));
-    }
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     const long long before = g->launches;
     int rc = GBP_OK;
     for (int r = 0; r < reps && rc == GBP_OK; ++r) {
-        if (fused) { rc = launch_fused(g, stages); continue; }
-        rc = launch_sweep(g, stages, pdl);
-        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1, 3, pdl);
+        rc = launch_sweep(g, stages);
+        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1, 3);
     }
     g->launches = before;  // capture does not execute
     cudaError_t e = cudaStreamEndCapture(g->stream, &graph);
@@ -658,15 +615,8 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         int rc = choose_tiling(cfg->tile_edges, cfg->lmk_block, L, F, &T, &lblock);
         if (rc != GBP_OK) return rc;
     }
-    if ((cfg->kernel_variant >= 5 && cfg->kernel_variant <= 9) || cfg->kernel_variant == 12) {
-        if (T == 128) { return fail(GBP_ERR_INVALID, "kernel_variants 5-9 and 12 need tile_edges 32 or 64"); }
-        if (cfg->kernel_variant == 5 || cfg->kernel_variant == 7 || cfg->kernel_variant == 8 || cfg->kernel_variant == 12) g->cam_w = CAM_MF;
-    }
-    if (cfg->kernel_variant == 10) {   // the ring kernel works on 32-edge tiles (one consumer warp each), factored messages
-        if (cfg->tile_edges != 0 && cfg->tile_edges != RING_T) { return fail(GBP_ERR_INVALID, "kernel_variant 10 needs tile_edges 0 or 32"); }
-        T = RING_T;
-        g->cam_w = CAM_MF;
-    }
+    if (cfg->kernel_variant < 0 || cfg->kernel_variant > 2) return fail(GBP_ERR_INVALID, "kernel_variant must be 0 (automatic), 1 or 2");
+    if (cfg->kernel_variant == 2 && T == 128) return fail(GBP_ERR_INVALID, "kernel_variant 2 (streaming build) needs tile_edges 32 or 64");
     g->T = T;
     GraphPlan plan;
     {
@@ -679,31 +629,23 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     g->h_file_of_factor = std::move(plan.file_of_factor);
     g->h_adj = std::move(plan.adj);
     g->h_slot_of_factor = std::move(plan.slot_of_factor);
-    const std::vector<int>&h_lmk_idx = plan.lmk_idx, &h_lmk_ptr = plan.lmk_ptr, &h_lmk_slots = plan.lmk_slots,
-                          &h_cam_tile_ptr = plan.cam_tile_ptr, &h_cam_tiles = plan.cam_tiles;
-    const std::vector<double>& h_z = plan.z;
-    if (cfg->kernel_variant == 11) {   // one-kernel iteration: needs an edge at every variable (its last edge finalises it)
-        bool all = T == 32 && g->n_tiles > 0 && g->n_tiles <= 8192;
-        for (int l = 0; all && l < L; ++l) all = h_lmk_ptr[l + 1] > h_lmk_ptr[l];
-        for (int c = 0; all && c < C; ++c) all = h_cam_tile_ptr[c + 1] > h_cam_tile_ptr[c];
-        g->fused_eligible = all;
-    }
-    {   // experiment switch (round 2 decides the default): early-start dependencies between the kernels of an iteration
-        const char* v = getenv("GBP_PDL");
-        g->pdl = v && atoi(v) != 0 && g->n_tiles <= 8192 && cfg->kernel_variant == 0;
-        // large graphs stream ~7 GB per sweep: factored keyframe messages (144 B less per edge), no descriptor wait in
-        // the prologue, and every CTA prefetches the streams of the tile ~38 k edges ahead into L2 (A/B on the 10 M-factor
-        // graph: flat optimum between 400 and 750 tiles of 64 edges; 1800 and more thrash L2)
-        g->auto_large = cfg->kernel_variant == 0 && g->n_tiles > 8192 && T <= 64;
-        if (g->auto_large) g->cam_w = CAM_MF;
-        const char* d = getenv("GBP_PF_DIST");
-        g->pf_dist = d ? std::max(0, atoi(d)) : ((g->auto_large || (cfg->kernel_variant == 12 && g->n_tiles > 8192)) ? 38400 / T : 0);
+    // Which build of the sweep kernel: graphs of more than 8192 tiles stream ~7 GB per sweep and get the streaming build
+    // (factored keyframe messages: 144 B less per edge; no descriptor wait in the prologue; every CTA prefetches the streams
+    // of the tile ~38 k edges ahead into L2 -- A/B on the 10 M-factor graph: flat optimum between 400 and 750 tiles of 64
+    // edges, 1800 and more thrash L2; the distance shrinks with the graph so that it stays below one wave of tiles).
+    g->streaming = cfg->kernel_variant == 2 || (cfg->kernel_variant == 0 && g->n_tiles > 8192 && T <= 64);
+    if (g->streaming) {
+        g->cam_w = CAM_MF;
+        g->pf_dist = g->n_tiles > 8192 ? (int)std::min<long long>(38400 / T, std::max(1, g->n_tiles / 32)) : 0;
     }
 
     // ---------------- device allocation + upload ----------------
     auto bail = [&](cudaError_t e, const char* what) { return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
     cudaError_t e;
     const size_t S = (size_t)g->n_slots;
+    Shell shell;
+    bool have_shell = false;   // an arena (and with the same shape: instantiated graphs) left by an earlier graph
+    size_t zero_off = 0, zero_end = 0;
     for (int pass = 0; pass < 2; ++pass) {   // pass 0 measures, pass 1 carves
         Arena& A = g->arena;
         A.used = 0;
@@ -712,39 +654,65 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         ALLOC(metric_out, 4); ALLOC(cam_mu, (size_t)C * 6); ALLOC(lmk_mu, (size_t)L * 3);
         g->snap_bytes = A.used;
         ALLOC(cam_belief, (size_t)C * CAM_B); ALLOC(lmk_belief, (size_t)L * LMK_B);
-        ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(iters, S); ALLOC(flags, S);
-        ALLOC(slot_of_factor, (size_t)F); ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F);
-        ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
-        ALLOC(z, S * 2); ALLOC(linpoint, S * 9); ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M); ALLOC(sigma2a, S);
-        ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
-        ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(tile_metric, tiles.size() * 3);
-        ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+        // upload region: the static tables of the graph, contiguous -> ONE host->device copy from a page-locked block
+        g->upload_off = A.used;
+        ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(z, S * 2); ALLOC(slot_of_factor, (size_t)F);
+        ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F); ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
         ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
+        g->upload_bytes = A.used - g->upload_off;
+        // zero region: everything gbp_ba_reset clears, contiguous -> ONE memset
+        zero_off = A.used;
+        ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M);
+        ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
+        ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+        zero_end = A.used;
+        ALLOC(iters, S); ALLOC(flags, S); ALLOC(linpoint, S * 9); ALLOC(sigma2a, S);
+        ALLOC(tile_metric, tiles.size() * 3);
 #undef ALLOC
         if (pass == 0) {
             A.size = A.used;
-            // GBP_POOL_ALLOC=1 (experiment for round 2): the arena comes from the device's stream-ordered memory pool with
-            // an unlimited release threshold, so that building graph after graph stops paying cudaMalloc / cudaFree
-            // (single create calls of 5-55 ms were seen in the end-to-end bench)
-            const char* pa = getenv("GBP_POOL_ALLOC");
-            g->arena_pooled = pa && atoi(pa) != 0;
-            if (g->arena_pooled) {
-                cudaMemPool_t pool;
-                unsigned long long keep = ~0ULL;
-                if ((e = cudaDeviceGetDefaultMemPool(&pool, device)) != cudaSuccess) return bail(e, "cudaDeviceGetDefaultMemPool");
-                if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return bail(e, "cudaMemPoolSetAttribute");
-                if ((e = cudaMallocAsync(reinterpret_cast<void**>(&A.base), A.size, g->stream)) != cudaSuccess) return bail(e, "cudaMallocAsync arena");
+            const ShapeKey key = make_key(g);
+            have_shell = cache_take(key, device, A.size, &shell);
+            if (have_shell) {
+                A.base = shell.arena; A.size = shell.arena_size;
+                g->stage = shell.stage; g->stage_bytes = shell.stage_bytes;
+                g->graphs = std::move(shell.graphs); g->snap_graphs = std::move(shell.snap_graphs); g->snap_ptr = shell.snap_ptr;
+                shell.arena = nullptr; shell.stage = nullptr;
             } else if ((e = cudaMalloc(reinterpret_cast<void**>(&A.base), A.size)) != cudaSuccess) {
+                A.base = nullptr;
                 return bail(e, "cudaMalloc arena");
             }
         }
     }
-#define UP(buf, vec) if (!(vec).empty() && (e = cudaMemcpyAsync(g->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload " #buf)
-    UP(tiles, tiles); UP(lmk_idx, h_lmk_idx); UP(z, h_z); UP(slot_of_factor, g->h_slot_of_factor);
-    UP(lmk_ptr, h_lmk_ptr); UP(lmk_slots, h_lmk_slots); UP(cam_tile_ptr, h_cam_tile_ptr); UP(cam_tiles, h_cam_tiles);
-#undef UP
-    if (C > 0 && (e = cudaMemcpyAsync(g->cam_mu0.p, cam_mu0, (size_t)C * 48, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload cam_mu0");
-    if (L > 0 && (e = cudaMemcpyAsync(g->lmk_mu0.p, lmk_mu0, (size_t)L * 24, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload lmk_mu0");
+    g->zero_off = zero_off;
+    g->zero_bytes = zero_end - zero_off;
+    {
+        struct Up { const void* src; size_t bytes; void* dst; };
+        const Up ups[] = {
+            {tiles.data(), tiles.size() * sizeof(Tile), g->tiles.p}, {plan.lmk_idx.data(), plan.lmk_idx.size() * 4, g->lmk_idx.p},
+            {plan.z.data(), plan.z.size() * 8, g->z.p}, {g->h_slot_of_factor.data(), g->h_slot_of_factor.size() * 4, g->slot_of_factor.p},
+            {plan.lmk_ptr.data(), plan.lmk_ptr.size() * 4, g->lmk_ptr.p}, {plan.lmk_slots.data(), plan.lmk_slots.size() * 4, g->lmk_slots.p},
+            {plan.cam_tile_ptr.data(), plan.cam_tile_ptr.size() * 4, g->cam_tile_ptr.p}, {plan.cam_tiles.data(), plan.cam_tiles.size() * 4, g->cam_tiles.p},
+            {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p}};
+        constexpr size_t STAGE_MAX = size_t(32) << 20;   // larger graphs upload table by table (a page-locked block that size costs more than it saves)
+        if (g->upload_bytes <= STAGE_MAX) {
+            if (g->stage_bytes < g->upload_bytes) {
+                if (g->stage) cudaFreeHost(g->stage);
+                g->stage = nullptr;
+                g->stage_bytes = 0;
+                const size_t want = std::max(g->upload_bytes, size_t(1) << 20);
+                if ((e = cudaHostAlloc(&g->stage, want, cudaHostAllocDefault)) != cudaSuccess) { g->stage = nullptr; return bail(e, "cudaHostAlloc staging block"); }
+                g->stage_bytes = want;
+            }
+            char* up0 = g->arena.base + g->upload_off;
+            for (const Up& u : ups)
+                if (u.bytes) memcpy(static_cast<char*>(g->stage) + (static_cast<char*>(u.dst) - up0), u.src, u.bytes);
+            if ((e = cudaMemcpyAsync(up0, g->stage, g->upload_bytes, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload of the graph tables");
+        } else {
+            for (const Up& u : ups)
+                if (u.bytes && (e = cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, g->stream)) != cudaSuccess) return bail(e, "upload of a graph table");
+        }
+    }
     {
         int rc = gbp_ba_reset(g);
         if (rc != GBP_OK) { return rc; }
@@ -767,13 +735,45 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F, const 
     }
 }
 
+int gbp_cache_configure(int32_t max_shells, int64_t max_arena_bytes) {
+    if (max_shells < 0 || max_arena_bytes < 0) return fail(GBP_ERR_INVALID, "negative cache limit");
+    std::vector<Shell> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cache_max_shells = max_shells;
+        g_cache_max_arena = (size_t)max_arena_bytes;
+        for (size_t i = 0; i < g_shells.size();) {
+            if (g_shells[i].arena_size > g_cache_max_arena) {
+                drop.push_back(std::move(g_shells[i]));
+                g_shells.erase(g_shells.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+        while ((int)g_shells.size() > g_cache_max_shells) {
+            drop.push_back(std::move(g_shells.front()));
+            g_shells.erase(g_shells.begin());
+        }
+    }
+    for (Shell& sh : drop) { cudaSetDevice(sh.device); sh.free_all(); }
+    return GBP_OK;
+}
+
+int gbp_cache_stats(int64_t out[6]) {
+    if (!out) return fail(GBP_ERR_INVALID, "null out");
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (int i = 0; i < 4; ++i) out[i] = g_cache_stats[i];
+    out[4] = (int64_t)g_shells.size();
+    size_t bytes = 0;
+    for (const Shell& sh : g_shells) bytes += sh.arena_size;
+    out[5] = (int64_t)bytes;
+    return GBP_OK;
+}
+
 int gbp_ba_reset(gbp_handle h) {
     CHECK_H(h);
     gbp_ba_graph* g = h;
-#define ZERO(buf) CU(cudaMemsetAsync(g->buf.p, 0, std::max<size_t>(g->buf.bytes(), 1), g->stream))
-    ZERO(msg_cam); ZERO(msg_lmk); ZERO(cam_prior); ZERO(lmk_prior); ZERO(cam_partial); ZERO(tile_partial);
-    ZERO(edge_max); ZERO(tile_max); ZERO(cam_max);
-#undef ZERO
+    if (g->zero_bytes) CU(cudaMemsetAsync(g->arena.base + g->zero_off, 0, g->zero_bytes, g->stream));   // messages, priors, partial sums, prior scans
     // beliefs: eta = Lambda = 0, mu = initial means; edges linearised at those means
     if (g->C > 0) init_belief_kernel<<<(g->C + 127) / 128, 128, 0, g->stream>>>(g->cam_mu0.p, g->C, 6, CAM_B, g->cam_belief.p, g->cam_mu.p);
     if (g->L > 0) init_belief_kernel<<<(g->L + 127) / 128, 128, 0, g->stream>>>(g->lmk_mu0.p, g->L, 3, LMK_B, g->lmk_belief.p, g->lmk_mu.p);
@@ -782,7 +782,6 @@ int gbp_ba_reset(gbp_handle h) {
         int rc = DISPATCH_T(g, launch_init_t);
         if (rc != GBP_OK) return rc;
     }
-    CU(cudaStreamSynchronize(g->stream));
     g->priors_set = false;
     return GBP_OK;
 }
@@ -805,8 +804,8 @@ int gbp_ba_layout(gbp_handle h, int64_t out[4]) {
     if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
     out[0] = h->cam_w;                 // doubles per stored factor->keyframe message: 27 (full) or 18 (factored)
     out[1] = h->pf_dist;               // L2 prefetch distance in tiles (0 = off)
-    out[2] = h->auto_large ? 7 : h->cfg.kernel_variant;   // sweep kernel build in use
-    out[3] = h->pdl ? 1 : 0;
+    out[2] = h->streaming ? 2 : 1;     // sweep kernel build in use (gbp_config.kernel_variant after the automatic choice)
+    out[3] = 0;                        // reserved
     return GBP_OK;
 }
 
@@ -991,8 +990,7 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
     constexpr int REPS = 8;
-    const bool fused = h->cfg.kernel_variant == 11 && h->fused_eligible;      // one launch per iteration
-    const int per_iter = fused ? 1 : (h->n_tiles > 0 ? 1 : 0) + 1;
+    const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
     int left = n_iters;
     if (left >= REPS && h->n_tiles <= 8192) {   // small graphs only: there the launch gaps are a visible share of an iteration
         cudaGraphExec_t exec8;

@@ -101,12 +101,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
-// start while its predecessor in the stream is still running; everything it reads from that predecessor must come after
-// pdl_wait() (returns once the predecessor grid has completed and its writes are visible; no-op for a normal launch).
-// pdl_launch_dependents() lets the NEXT kernel of the stream start early in the same way.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 
 // scalars of the edge (none of them is written by belief_kernel); returns the landmark index for the gather
 __device__ __forceinline__ int load_edge_scalars(const SweepParams& p, long long e, EdgeRegs& r) {
@@ -121,44 +116,23 @@ __device__ __forceinline__ int load_edge_scalars(const SweepParams& p, long long
 }
 
 // the dependent gather: 96 B landmark belief row (six 16 B loads)
-template <bool HINTS>
 __device__ __forceinline__ void gather_lmk_belief(const SweepParams& p, int lmk, EdgeRegs& r) {
     const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
-    uint64_t pol = 0;
-    if (HINTS) pol = policy_evict_last();
+    const uint64_t pol = policy_evict_last();
 #pragma unroll
     for (int k = 0; k < LMK_B / 2; ++k) {
-        const double2 v = HINTS ? ldg_hint(src + k, pol) : __ldg(src + k);
+        const double2 v = ldg_hint(src + k, pol);
         r.bl[2 * k] = v.x;
         r.bl[2 * k + 1] = v.y;
     }
 }
 
-template <bool HINTS>
 __device__ __forceinline__ void load_edge_regs(const SweepParams& p, long long e, EdgeRegs& r) {
     const int lmk = load_edge_scalars(p, e, r);
-    gather_lmk_belief<HINTS>(p, lmk, r);
+    gather_lmk_belief(p, lmk, r);
 }
 
-// Sum of v[0..26] over the 32 lanes of a warp; lane c (< 27) returns column c.  Reduce-scatter butterfly: at distance
-// 16, 8, 4, 2, 1 a lane keeps the half of its columns selected by the corresponding bit of its lane id and adds the
-// partner's copy of that half: 31 doubles exchanged instead of 27 x 5.  Fixed tree => deterministic.
-__device__ __forceinline__ double warp_column_sums27(const double* full, int lane) {
-    double v[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = k < CAM_M ? full[k] : 0.0;
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const bool up = (lane & w) != 0;
-#pragma unroll
-        for (int j = 0; j < w; ++j) {
-            const double keep = up ? v[w + j] : v[j];
-            const double give = up ? v[j] : v[w + j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, give, w);
-        }
-    }
-    return v[0];
-}
+
 
 // column sums of the tile's (new) messages to its keyframe -> tile_partial[tile][27]
 template <int T>
@@ -181,50 +155,48 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tile,
     }
 }
 
+
 // ----------------------------------------------------------------------------------------
 // K1-K3 (+ the keyframe half of K4): robustify -> relinearise -> factor-to-variable messages
 // -> per-tile sum of the messages to the keyframe.   One CTA per tile, one thread per edge.
 // Replaces gbp/gbp.py:82-84,296-332 / 64-80,267-294 / 46-54,334-373 for reprojection factors.
 //
-// sweep_kernel      : tile rows staged by TMA bulk copies (one elected thread, mbarrier
-//                     completion); every thread issues its gathers (landmark index -> 96 B belief
-//                     row) BEFORE waiting, so all of a tile's DRAM round trips overlap; new rows
-//                     leave by bulk stores.
-// sweep_kernel_ldg  : first version (cooperative LDG/STS copies), kept for A/B measurements.
+// The tile's row blocks are staged by TMA bulk copies (one elected thread, mbarrier completion); every
+// thread issues its gathers (landmark index -> 96 B belief row) BEFORE waiting, so all of a tile's DRAM
+// round trips overlap; new rows leave by bulk stores.  Compiled for 384 resident threads per SM
+// (<= 170 registers, no spills; a 128-register build for 16 warps per SM was measured slower).
+//
+// STREAM = false  graphs that live in L2 (up to 8192 tiles): full 27-double keyframe message rows, the bulk
+//                 copies are sized by the tile descriptor.
+// STREAM = true   HBM-bound graphs: (i) the keyframe messages live in HBM with their rank-2 precision FACTORED
+//                 (18 doubles per row instead of 27: 144 B less traffic per edge and sweep), the threads expand
+//                 them into s_full for the keyframe-side sum; (ii) EARLY ISSUE: a tile owns T slots (padding
+//                 slots hold landmark 0, zero rows, iters = -1), so the bulk loads fetch all T rows and every
+//                 thread loads its scalars and gathers its landmark row unconditionally at once; the descriptor
+//                 (count, keyframe) arrives in parallel and is only needed for the keyframe row and the stores
+//                 (dependent DRAM round trips before the edge code: 3 -> 2); (iii) FAR-AHEAD L2 PREFETCH of the
+//                 streams of tile + pf_dist.  Measured on the 10 M-factor graph: 1.257 -> 0.995 ms per launch.
+// Experiments that lost against this kernel (persistent double-buffered CTAs, a warp-specialised producer /
+// consumer ring, cooperative LDG staging, 128-register builds, register-level column sums, programmatic
+// dependent launches, a completion-counter one-kernel iteration) are in the git history and profiles/README.md.
 // ----------------------------------------------------------------------------------------
-// Compiled for 384 resident threads per SM (<= 170 registers, no spills).  OCC = 1: 512 threads per SM (128 registers,
-// a few spilled doubles) -- measured SLOWER (1.32 vs 1.25 ms on the 10 M-factor graph), kept as kernel_variant 3 for A/B.
-// PDL = true (small, latency-bound graphs; launched with the programmatic-serialisation attribute): the prologue -- barrier
-// init, bulk loads of the tile's rows, the edge's scalars -- runs while belief_kernel of the previous iteration is still
-// finishing; only the belief rows are read after pdl_wait().  Everything read before the wait was written by the sweep of
-// the previous iteration, which had completed before that belief_kernel released its dependents.
-// FACT = true (kernel_variant 5): the keyframe messages live in HBM with their rank-2 precision factored (18 doubles per
-// row instead of 27: 144 B less traffic per edge and sweep); the threads expand them into s_full for the keyframe-side sum.
-// EARLY = true (kernel_variants 6-9): nothing on the critical path waits for the tile descriptor.  A tile owns T slots
-// (padding slots hold landmark 0, zero rows, iters = -1), so the bulk loads fetch all T rows and every thread loads its
-// scalars and gathers its landmark row unconditionally at once; the descriptor (count, keyframe) arrives in parallel
-// and is only needed for the keyframe row and the stores.  Dependent DRAM round trips before the edge code: 3 -> 2.
-// REGSUM = true (kernel_variant 12, with FACT): the keyframe-side sums of the tile are formed in registers by the shuffle
-// reduce-scatter above instead of through full-form rows in shared memory (no s_full: 13.8 KB less per 64-edge CTA, 27
-// shared stores per thread and one CTA barrier less); the warps' column sums meet in s_red.
-template <int T, bool ROBUST, bool HINTS, int OCC = 0, bool PDL = false, bool FACT = false, bool EARLY = false, bool REGSUM = false>
-__global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T) sweep_kernel(const SweepParams p) {
-    static_assert(!REGSUM || FACT, "register column sums are written for the factored layout");
+template <int T, bool ROBUST, bool STREAM>
+__global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int CW = FACT ? CAM_MF : CAM_M;
+    constexpr int CW = STREAM ? CAM_MF : CAM_M;
     double* s_mc = smem;                 // [T][27]  (or [T][18] factored)
     double* s_ml = s_mc + T * CW;        // [T][9]
     double* s_lp = s_ml + T * LMK_M;     // [T][9]
     double* s_cb = s_lp + T * 9;         // [33] keyframe belief (+pad to 34)
     double* s_red = s_cb + 34;           // [T/32][27]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);
-    double* s_full = s_red + (T / 32) * CAM_M + 2;   // [T][27] full-form messages of the tile (FACT only)
+    double* s_full = s_red + (T / 32) * CAM_M + 2;   // [T][27] full-form messages of the tile (STREAM only)
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
     const long long base = (long long)tile * T;
     EdgeRegs r;
-    if (EARLY) {
+    if (STREAM) {
         if (tid == 0) {
             mbar_init(bar, 1);          // only this thread touches the barrier before the __syncthreads below
             mbar_expect_tx(bar, (uint32_t)T * (CW + LMK_M + 9) * 8);
@@ -234,7 +206,7 @@ __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T
             bulk_g2s_hint(s_lp, p.linpoint + base * 9, (uint32_t)T * 72, bar, pol);
         }
         const int lmk = load_edge_scalars(p, base + tid, r);
-        gather_lmk_belief<HINTS>(p, lmk, r);
+        gather_lmk_belief(p, lmk, r);
         // Far-ahead L2 prefetch: CTAs start roughly in tile order, so the streams of tile + pf_dist are fetched from HBM
         // now and are L2 hits when that tile's CTA asks for them (its loads then cost an L2 round trip, not a loaded-HBM one)
         if (p.pf_dist > 0 && tid >= 1 && tid <= 8) {
@@ -258,426 +230,47 @@ __global__ void __launch_bounds__(T, (OCC == 1 ? 512 : OCC == 2 ? 448 : 384) / T
     const int n = tl.count;
     const int n_even = (n + 1) & ~1;     // bulk copies move multiples of 16 B; the extra row is tile padding
 
-    if (!EARLY) {
+    if (!STREAM) {
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
-    }
-    if (PDL) pdl_launch_dependents();   // belief_kernel behind us may be scheduled; it waits for this grid before it reads
-    if (!EARLY && tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)n_even * (CW + LMK_M + 9) * 8);
-        if (HINTS) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)n_even * (CW + LMK_M + 9) * 8);
             const uint64_t pol = policy_evict_first();
             bulk_g2s_hint(s_mc, p.msg_cam + base * CW, (uint32_t)n_even * CW * 8, bar, pol);
             bulk_g2s_hint(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar, pol);
             bulk_g2s_hint(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar, pol);
-        } else {
-            bulk_g2s(s_mc, p.msg_cam + base * CW, (uint32_t)n_even * CW * 8, bar);
-            bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
-            bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
         }
     }
-    if (EARLY) {
-        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
-    } else if (PDL) {
-        int lmk = 0;
-        if (tid < n) lmk = load_edge_scalars(p, base + tid, r);
-        pdl_wait();           // beliefs of the previous iteration are complete and visible from here on
-        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
-        if (tid < n) gather_lmk_belief<HINTS>(p, lmk, r);
-    } else {
-        for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
-        if (tid < n) load_edge_regs<HINTS>(p, base + tid, r);
-    }
+    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
+    if (!STREAM && tid < n) load_edge_regs(p, base + tid, r);
     __syncthreads();          // s_cb visible
     mbar_wait(bar, 0);        // bulk loads landed
 
     bool relin = false;
-    double full[REGSUM ? CAM_M : 1];
-    if (tid < n) {
-        relin = edge_sweep<ROBUST, FACT>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
-                                         REGSUM ? full : (FACT ? s_full + tid * CAM_M : nullptr));
-    } else if (REGSUM) {
-#pragma unroll
-        for (int j = 0; j < (REGSUM ? CAM_M : 1); ++j) full[j] = 0.0;
-    }
-    if (REGSUM && (p.stages & ST_BELIEFS)) {     // whole warps take part (tiles are padded to T threads)
-        const double col = warp_column_sums27(full, tid & 31);
-        if ((tid & 31) < CAM_M) s_red[(tid >> 5) * CAM_M + (tid & 31)] = col;
-    }
+    if (tid < n)
+        relin = edge_sweep<ROBUST, STREAM>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
+                                           STREAM ? s_full + tid * CAM_M : nullptr);
     fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
     if (tid == 0) {
-        if (HINTS) {
-            // the message rows of the landmark are gathered again by belief_kernel: only the big keyframe rows
-            // and the linearisation points are marked evict_first
-            const uint64_t pol = policy_evict_first();
-            if (p.stages & ST_MESSAGES) {
-                bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
-                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
-            }
-            if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
-        } else {
-            if (p.stages & ST_MESSAGES) {
-                bulk_s2g(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8);
-                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
-            }
-            if (any_relin) bulk_s2g(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72);
+        // the message rows of the landmark are gathered again by belief_kernel: only the big keyframe rows
+        // and the linearisation points are marked evict_first
+        const uint64_t pol = policy_evict_first();
+        if (p.stages & ST_MESSAGES) {
+            bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
+            bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
         }
+        if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
         bulk_commit();
     }
-    if (REGSUM) {
-        if ((p.stages & ST_BELIEFS) && tid < CAM_M) {        // s_red was completed before the barrier above
-            double acc = s_red[tid];
-#pragma unroll
-            for (int g = 1; g < T / 32; ++g) acc += s_red[g * CAM_M + tid];
-            p.tile_partial[(long long)tile * CAM_M + tid] = acc;
-        }
-    } else if (p.stages & ST_BELIEFS) {
-        tile_column_sums<T>(p, tile, n, FACT ? s_full : s_mc, s_red);
-    }
+    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, STREAM ? s_full : s_mc, s_red);
     if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
 }
 
-// ----------------------------------------------------------------------------------------
-// Persistent, double-buffered variant (kernel_variant 4): a CTA walks tiles blockIdx.x, +gridDim.x, ... and
-// while it computes tile i from stage s it already has tile i+1 in flight into stage s^1 (bulk copies on
-// that stage's mbarrier; the per-edge scalars and the gathered landmark belief row wait in registers).
-// Fewer resident warps (8 per SM instead of 12: 216 registers, two stages of shared memory), but none of them
-// ever waits for its tile.  MEASURED SLOWER (1.38 vs 1.18 ms on the 10 M-factor graph): with 8 warps the SM is
-// bound by the latency of the dependent fp64 chains, not by memory.  Kept for A/B runs only.
-// ----------------------------------------------------------------------------------------
-template <int T>
-constexpr size_t sweep_persistent_smem_bytes() {
-    return sizeof(double) * (size_t)(2 * T * (CAM_M + LMK_M + 9) + 2 * 34 + (T / 32) * CAM_M + 2 /* two mbarriers */);
-}
-
-template <int T, bool ROBUST>
-__global__ void __launch_bounds__(T, 256 / T) sweep_kernel_persistent(const SweepParams p) {
-    extern __shared__ __align__(128) double smem[];
-    constexpr int STAGE = T * (CAM_M + LMK_M + 9);
-    double* s_cb = smem + 2 * STAGE;         // [2][34]
-    double* s_red = s_cb + 2 * 34;           // [T/32][27]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);   // [2]
-    const int tid = threadIdx.x;
-    int tile = blockIdx.x;
-    if (tile >= p.n_tiles) return;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-    }
-    __syncthreads();
-    const uint64_t pol = policy_evict_first();
-
-    auto issue = [&](int t, const Tile& tl, int s) {   // thread 0: bulk loads of tile t into stage s
-        double* st = smem + s * STAGE;
-        const long long base = (long long)t * T;
-        const uint32_t n_even = (uint32_t)((tl.count + 1) & ~1);
-        mbar_expect_tx(&bar[s], n_even * (CAM_M + LMK_M + 9) * 8);
-        bulk_g2s_hint(st, p.msg_cam + base * CAM_M, n_even * CAM_M * 8, &bar[s], pol);
-        bulk_g2s_hint(st + T * CAM_M, p.msg_lmk + base * LMK_M, n_even * LMK_M * 8, &bar[s], pol);
-        bulk_g2s_hint(st + T * (CAM_M + LMK_M), p.linpoint + base * 9, n_even * 72, &bar[s], pol);
-    };
-
-    Tile tl_cur = p.tiles[tile];
-    EdgeRegs r_cur;
-    if (tid == 0) issue(tile, tl_cur, 0);
-    if (tid < tl_cur.count) load_edge_regs<true>(p, (long long)tile * T + tid, r_cur);
-    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl_cur.cam * CAM_B + i];
-
-    for (int it = 0;; ++it) {
-        const int s = it & 1;
-        const int next = tile + (int)gridDim.x;
-        const bool has_next = next < p.n_tiles;
-        Tile tl_next = tl_cur;
-        EdgeRegs r_next;
-        if (has_next) {
-            tl_next = p.tiles[next];
-            if (tid == 0) {
-                bulk_wait_read0();             // the stores of tile it-1 have finished reading stage s^1
-                issue(next, tl_next, s ^ 1);
-            }
-            if (tid < tl_next.count) load_edge_regs<true>(p, (long long)next * T + tid, r_next);
-            for (int i = tid; i < CAM_B; i += T) s_cb[(s ^ 1) * 34 + i] = p.cam_belief[(long long)tl_next.cam * CAM_B + i];
-        }
-        __syncthreads();                        // s_cb[s] (written one iteration ago) visible to everyone
-        mbar_wait(&bar[s], (uint32_t)((it >> 1) & 1));
-
-        double* s_mc = smem + s * STAGE;
-        double* s_ml = s_mc + T * CAM_M;
-        double* s_lp = s_ml + T * LMK_M;
-        const int n = tl_cur.count;
-        const long long base = (long long)tile * T;
-        bool relin = false;
-        if (tid < n) relin = edge_sweep<ROBUST>(p, base + tid, r_cur, s_cb + s * 34, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
-        fence_async_smem();
-        const int any_relin = __syncthreads_or(relin ? 1 : 0);
-        if (tid == 0) {
-            const uint32_t n_even = (uint32_t)((n + 1) & ~1);
-            if (p.stages & ST_MESSAGES) {
-                bulk_s2g_hint(p.msg_cam + base * CAM_M, s_mc, n_even * CAM_M * 8, pol);
-                bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, n_even * LMK_M * 8);
-            }
-            if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, n_even * 72, pol);
-            bulk_commit();
-        }
-        if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
-        if (!has_next) break;
-        tile = next;
-        tl_cur = tl_next;
-        r_cur = r_next;
-    }
-    if (tid == 0) bulk_wait_read0();
-}
-
-// ----------------------------------------------------------------------------------------
-// Warp-specialised persistent sweep (kernel_variant 10; factored keyframe messages, 32-edge tiles).
-//
-// One CTA per SM: warp 0 is the PRODUCER, warps 1..RING_CONSUMERS are CONSUMERS, one tile (= one warp of edges) each at a
-// time.  Shared memory is a ring of RING_SLOTS tile slots; a slot holds everything a tile needs -- message rows,
-// linearisation points, the per-edge scalars (landmark index, iters, flags, z, adaptive variance), the gathered
-// landmark belief rows and the keyframe belief row -- so a consumer never waits for global memory: while
-// RING_CONSUMERS slots are being computed, the other slots are in flight (RING_SLOTS - RING_CONSUMERS tiles, ~70 KB per
-// SM: the bandwidth-delay product of HBM3e at ~1.5 us).  The default kernel has 12 warps per SM that each spend a
-// third of their life waiting for their tile (long_scoreboard 2.8 - 4.9 of 9 cycles per instruction, see profiles/).
-//
-//   full_a[slot]  bulk copies of the tile's contiguous streams landed (tx count)        producer -> producer, consumer
-//   full_b[slot]  gather of the 96 B landmark rows (cp.async, needs the indices of
-//                 full_a) and the keyframe row landed; descriptor written               producer -> consumer
-//   empty[slot]   consumer finished: rows stored (bulk store has read the slot)         consumer -> producer
-//
-// The producer issues the gather of tile k - RING_LAG in the same loop iteration as the bulk copies of tile k, so it
-// never blocks on the first round trip of a tile.  Keyframe-side sums: the warp's 27 column sums are formed in
-// registers by a shuffle reduce-scatter (lane c ends with column c), no shared memory.
-// ----------------------------------------------------------------------------------------
-constexpr int RING_T = 32;            // edges per tile (one consumer warp)
-constexpr int RING_SLOTS = 16;
-constexpr int RING_CONSUMERS = 11;    // 12 warps x 32 lanes x 168 registers = the register file
-constexpr int RING_LAG = 3;
-constexpr int RING_BEL_STRIDE = 14;   // doubles per gathered landmark row in the slot (12 + pad: conflict-free 16 B reads)
-
-struct RingSlot {                      // byte offsets inside a slot; every stream starts 16 B aligned
-    static constexpr int MC = 0;                                   // [32][18] factored keyframe messages
-    static constexpr int ML = MC + RING_T * CAM_MF * 8;            // [32][9]
-    static constexpr int LP = ML + RING_T * LMK_M * 8;             // [32][9]
-    static constexpr int BEL = LP + RING_T * 9 * 8;                // [32][14] gathered landmark belief rows
-    static constexpr int Z = BEL + RING_T * RING_BEL_STRIDE * 8;   // [32][2]
-    static constexpr int VAR = Z + RING_T * 16;                    // [32] adaptive variance
-    static constexpr int IDX = VAR + RING_T * 8;                   // [32] i32
-    static constexpr int ITERS = IDX + RING_T * 4;
-    static constexpr int FLAGS = ITERS + RING_T * 4;
-    static constexpr int CB = FLAGS + RING_T * 4;                  // [34] keyframe belief row
-    static constexpr int META = CB + 34 * 8;                       // Tile (count, cam) + pad
-    static constexpr int BYTES = META + 16;
-};
-static_assert(RingSlot::BYTES % 16 == 0, "slots must keep 16 B alignment");
-constexpr size_t ring_smem_bytes() { return (size_t)RING_SLOTS * RingSlot::BYTES + 3 * RING_SLOTS * 8; }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-// arrive on `bar` once every cp.async issued so far by this thread has landed (counted in the barrier's expected arrivals)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <bool ROBUST>
-__global__ void __launch_bounds__(32 * (RING_CONSUMERS + 1), 1) sweep_ring_kernel(const SweepParams p) {
-    extern __shared__ __align__(128) unsigned char ring[];
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(ring + (size_t)RING_SLOTS * RingSlot::BYTES);
-    uint64_t* full_b = full_a + RING_SLOTS;
-    uint64_t* empty = full_b + RING_SLOTS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int first = blockIdx.x, stride = gridDim.x;
-    const int nk = first < p.n_tiles ? (p.n_tiles - first + stride - 1) / stride : 0;   // tiles of this CTA
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < RING_SLOTS; ++s) {
-            mbar_init(&full_a[s], 1);
-            mbar_init(&full_b[s], 33);      // 32 cp.async completions + the producer's release of the descriptor
-            mbar_init(&empty[s], 1);
-        }
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer
-        const uint64_t pol_stream = policy_evict_first();
-        const uint64_t pol_keep = policy_evict_last();
-        (void)pol_keep;
-        Tile tl_next{0, 0};
-        if (nk > 0) tl_next = p.tiles[first];
-        constexpr uint32_t BYTES_A = RING_T * (CAM_MF + LMK_M + 9) * 8 + RING_T * (16 + 4 + 4 + 4) + (ROBUST ? RING_T * 8 : 0);
-        for (int k = 0; k < nk + RING_LAG; ++k) {
-            // ---- gather of tile k - LAG (its indices landed long ago)
-            const int kb = k - RING_LAG;
-            if (kb >= 0) {
-                const int slot = kb % RING_SLOTS;
-                unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
-                mbar_wait(&full_a[slot], (uint32_t)((kb / RING_SLOTS) & 1));
-                const int lmk = reinterpret_cast<const int*>(S + RingSlot::IDX)[lane];
-                const double* src = p.lmk_belief + (long long)lmk * LMK_B;
-                double* dst = reinterpret_cast<double*>(S + RingSlot::BEL) + lane * RING_BEL_STRIDE;
-#pragma unroll
-                for (int j = 0; j < LMK_B / 2; ++j) cp_async16(dst + 2 * j, src + 2 * j);
-                cp_async_arrive_noinc(&full_b[slot]);
-                if (lane == 0) mbar_arrive(&full_b[slot]);
-            }
-            // ---- bulk copies of tile k
-            if (k < nk) {
-                const int slot = k % RING_SLOTS, use = k / RING_SLOTS;
-                unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
-                if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
-                const int tile = first + k * stride;
-                const long long base = (long long)tile * RING_T;
-                const Tile tl = tl_next;
-                if (k + 1 < nk) tl_next = p.tiles[tile + stride];      // arrives during the coming iterations
-                if (lane == 0) {
-                    *reinterpret_cast<Tile*>(S + RingSlot::META) = tl;
-                    mbar_expect_tx(&full_a[slot], BYTES_A);
-                    bulk_g2s_hint(S + RingSlot::MC, p.msg_cam + base * CAM_MF, RING_T * CAM_MF * 8, &full_a[slot], pol_stream);
-                    bulk_g2s_hint(S + RingSlot::ML, p.msg_lmk + base * LMK_M, RING_T * LMK_M * 8, &full_a[slot], pol_stream);
-                    bulk_g2s_hint(S + RingSlot::LP, p.linpoint + base * 9, RING_T * 72, &full_a[slot], pol_stream);
-                    bulk_g2s(S + RingSlot::Z, p.z + base * 2, RING_T * 16, &full_a[slot]);
-                    bulk_g2s(S + RingSlot::IDX, p.lmk_idx + base, RING_T * 4, &full_a[slot]);
-                    bulk_g2s(S + RingSlot::ITERS, p.iters + base, RING_T * 4, &full_a[slot]);
-                    bulk_g2s(S + RingSlot::FLAGS, p.flags + base, RING_T * 4, &full_a[slot]);
-                    if (ROBUST) bulk_g2s(S + RingSlot::VAR, p.sigma2a + base, RING_T * 8, &full_a[slot]);
-                }
-                // far-ahead L2 prefetch of a later tile's streams (any CTA may own it: L2 is shared)
-                if (p.pf_dist > 0 && lane >= 1 && lane <= 8) {
-                    const long long tp = (long long)tile + p.pf_dist;
-                    if (tp < p.n_tiles) {
-                        const long long b = tp * RING_T;
-                        switch (lane) {
-                            case 1: bulk_prefetch_l2(p.msg_cam + b * CAM_MF, RING_T * CAM_MF * 8); break;
-                            case 2: bulk_prefetch_l2(p.msg_lmk + b * LMK_M, RING_T * LMK_M * 8); break;
-                            case 3: bulk_prefetch_l2(p.linpoint + b * 9, RING_T * 72); break;
-                            case 4: bulk_prefetch_l2(p.z + b * 2, RING_T * 16); break;
-                            case 5: bulk_prefetch_l2(p.lmk_idx + b, RING_T * 4); break;
-                            case 6: bulk_prefetch_l2(p.iters + b, RING_T * 4); break;
-                            case 7: bulk_prefetch_l2(p.flags + b, RING_T * 4); break;
-                            default: if (ROBUST) bulk_prefetch_l2(p.sigma2a + b, RING_T * 8); break;
-                        }
-                    }
-                }
-                // keyframe belief row: 33 doubles, 8 B copies (rows are only 8 B aligned)
-                const double* crow = p.cam_belief + (long long)tl.cam * CAM_B;
-                double* cdst = reinterpret_cast<double*>(S + RingSlot::CB);
-                cp_async8(cdst + lane, crow + lane);
-                if (lane == 0) cp_async8(cdst + 32, crow + 32);
-                // (covered by the cp.async arrive of this tile's gather, RING_LAG iterations from now)
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ consumers
-        for (int k = warp - 1; k < nk; k += RING_CONSUMERS) {
-            const int slot = k % RING_SLOTS;
-            const uint32_t par = (uint32_t)((k / RING_SLOTS) & 1);
-            unsigned char* S = ring + (size_t)slot * RingSlot::BYTES;
-            mbar_wait(&full_a[slot], par);
-            mbar_wait(&full_b[slot], par);
-            const Tile tl = *reinterpret_cast<const Tile*>(S + RingSlot::META);
-            const int n = tl.count;
-            const int tile = first + k * stride;
-            const long long base = (long long)tile * RING_T;
-            double* s_mc = reinterpret_cast<double*>(S + RingSlot::MC);
-            double* s_ml = reinterpret_cast<double*>(S + RingSlot::ML);
-            double* s_lp = reinterpret_cast<double*>(S + RingSlot::LP);
-            EdgeRegs r;
-            r.it = reinterpret_cast<const int*>(S + RingSlot::ITERS)[lane];
-            r.fl = reinterpret_cast<const int*>(S + RingSlot::FLAGS)[lane];
-            r.var = ROBUST ? reinterpret_cast<const double*>(S + RingSlot::VAR)[lane] : p.var0;
-            const double2 zz = reinterpret_cast<const double2*>(S + RingSlot::Z)[lane];
-            r.z[0] = zz.x;
-            r.z[1] = zz.y;
-            const double2* b2 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(S + RingSlot::BEL) + lane * RING_BEL_STRIDE);
-#pragma unroll
-            for (int j = 0; j < LMK_B / 2; ++j) {
-                const double2 v = b2[j];
-                r.bl[2 * j] = v.x;
-                r.bl[2 * j + 1] = v.y;
-            }
-            double full[CAM_M];
-            bool relin = false;
-            if (lane < n) {
-                relin = edge_sweep<ROBUST, true>(p, base + lane, r, reinterpret_cast<const double*>(S + RingSlot::CB), s_lp + lane * 9,
-                                                 s_mc + lane * CAM_MF, s_ml + lane * LMK_M, full);
-            } else {        // padding lanes add nothing to the keyframe-side sums (zeroed here, not before: registers)
-#pragma unroll
-                for (int j = 0; j < CAM_M; ++j) full[j] = 0.0;
-            }
-            fence_async_smem();      // generic-proxy writes of the new rows -> visible to the bulk-copy engine
-            const unsigned any_relin = __ballot_sync(0xffffffffu, relin);    // also the warp-level barrier before the stores
-            if (lane == 0) {
-                const uint32_t n_even = (uint32_t)((n + 1) & ~1);
-                const uint64_t pol = policy_evict_first();
-                if (p.stages & ST_MESSAGES) {
-                    bulk_s2g_hint(p.msg_cam + base * CAM_MF, s_mc, n_even * CAM_MF * 8, pol);
-                    bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, n_even * LMK_M * 8);
-                }
-                if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, n_even * 72, pol);
-                bulk_commit();
-            }
-            if (p.stages & ST_BELIEFS) {
-                const double col = warp_column_sums27(full, lane);
-                if (lane < CAM_M) p.tile_partial[(long long)tile * CAM_M + lane] = col;
-            }
-            if (lane == 0) {
-                bulk_wait_read0();          // the engine has read the slot
-                mbar_arrive(&empty[slot]);  // ... which every lane of this warp finished using before the ballot above
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <int T, bool ROBUST>
-__global__ void __launch_bounds__(T) sweep_kernel_ldg(const SweepParams p) {
-    extern __shared__ __align__(128) double smem[];
-    double* s_mc = smem;
-    double* s_ml = s_mc + T * CAM_M;
-    double* s_lp = s_ml + T * LMK_M;
-    double* s_cb = s_lp + T * 9;
-    double* s_red = s_cb + 34;
-
-    const int tile = blockIdx.x;
-    const int tid = threadIdx.x;
-    const Tile tl = p.tiles[tile];
-    const int n = tl.count;
-    const long long base = (long long)tile * T;
-
-    coop_copy<T>(s_mc, p.msg_cam + base * CAM_M, n * CAM_M);
-    coop_copy<T>(s_ml, p.msg_lmk + base * LMK_M, n * LMK_M);
-    coop_copy<T>(s_lp, p.linpoint + base * 9, n * 9);
-    for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];
-    __syncthreads();
-
-    bool relin = false;
-    if (tid < n) {
-        EdgeRegs r;
-        load_edge_regs<false>(p, base + tid, r);
-        relin = edge_sweep<ROBUST>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CAM_M, s_ml + tid * LMK_M);
-    }
-    const int any_relin = __syncthreads_or(relin ? 1 : 0);
-
-    if (p.stages & ST_MESSAGES) {
-        coop_copy<T>(p.msg_cam + base * CAM_M, s_mc, n * CAM_M);
-        coop_copy<T>(p.msg_lmk + base * LMK_M, s_ml, n * LMK_M);
-    }
-    if (any_relin) coop_copy<T>(p.linpoint + base * 9, s_lp, n * 9);
-    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tile, n, s_mc, s_red);
-}
-
-template <int T, bool FACT = false, bool REGSUM = false>
+template <int T, bool STREAM>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(double) * (size_t)(T * ((FACT ? (REGSUM ? CAM_MF : CAM_MF + CAM_M) : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
+    return sizeof(double) * (size_t)(T * ((STREAM ? CAM_MF + CAM_M : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -704,7 +297,6 @@ struct BeliefParams {
     double* lmk_mu;          // [L][3]
     int L, C, finalise;
     int parts;               // bit0: keyframe CTAs, bit1: landmark CTAs (multi-GPU runs them as two launches)
-    int pdl;                 // launched with programmatic serialisation behind sweep_kernel
 };
 
 __device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out) {
@@ -744,10 +336,6 @@ __device__ __forceinline__ void load_row9(const double* __restrict__ row, bool e
 template <int LMK_LANES>
 __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     constexpr int LMK_PER_CTA = 128 / LMK_LANES;
-    if (p.pdl) {
-        pdl_wait();                 // every message / tile partial of this iteration's sweep is complete and visible
-        pdl_launch_dependents();    // only now: the next sweep's prologue reads rows that sweep wrote
-    }
     const int cam_blocks = (p.parts & 1) ? (p.C + 3) / 4 : 0;
     if ((int)blockIdx.x < cam_blocks) {
         // ---- keyframes first in the grid: their serial tile loops overlap the landmark CTAs
@@ -840,160 +428,6 @@ __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restric
     cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B, cam_mu + (long long)c * 6);
 }
 
-// ----------------------------------------------------------------------------------------
-// One-kernel iteration for small (L2-resident, latency-bound) graphs -- kernel_variant 11, NOT YET RUN ON HARDWARE.
-//
-// fr1desk spends 9 us per iteration in two ~4.5 us kernels whose length is set by dependent latencies, not by work.
-// This kernel appends the belief update to the sweep without a grid-wide barrier: a variable's belief may be rewritten
-// as soon as ALL of its edges have been swept -- exactly the edges that read it -- so the warp that sweeps the LAST
-// tile of a keyframe (last edge of a landmark) finalises that keyframe (landmark).  "Last" is found with one
-// atomic counter per variable (incremented after the tile's results are globally visible; reset by the finaliser for
-// the next launch).  Nobody ever waits, so there is nothing to deadlock; the Jacobi semantics of
-// synchronous_iteration (gbp/gbp.py:86-92: all messages of a sweep use the beliefs of the previous one) hold because
-// every reader of a belief row has finished before the row is rewritten.  Sums run in the same fixed orders as
-// belief_kernel<32> (CSR order per landmark, tile order per keyframe), independent of which warp does them, so the
-// result is deterministic and equal to the two-kernel path.
-//   grid = tiles, block = 32 (one warp per 32-edge tile); full-form message rows; every variable has degree >= 1.
-// ----------------------------------------------------------------------------------------
-struct FusedParams {
-    SweepParams sweep;
-    const double* lmk_prior;
-    const double* cam_prior;
-    double* lmk_belief_out;        // same arrays as sweep.lmk_belief / cam_belief, writable
-    double* cam_belief_out;
-    double* cam_partial;
-    double* cam_mu;
-    double* lmk_mu;
-    const int* lmk_ptr;
-    const int* lmk_slots;
-    const int* cam_tile_ptr;
-    const int* cam_tiles;
-    int* lmk_done;                 // [L] edges of the landmark swept so far in this launch (0 between launches)
-    int* cam_done;                 // [C] tiles of the keyframe swept so far
-};
-
-template <bool ROBUST>
-__global__ void __launch_bounds__(32, 12) sweep_fused_kernel(const FusedParams fp) {
-    constexpr int T = 32;
-    const SweepParams& p = fp.sweep;
-    extern __shared__ __align__(128) double smem[];
-    double* s_mc = smem;                 // [T][27]
-    double* s_ml = s_mc + T * CAM_M;     // [T][9]
-    double* s_lp = s_ml + T * LMK_M;     // [T][9]
-    double* s_cb = s_lp + T * 9;         // [34]
-    double* s_red = s_cb + 34;           // [27]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + CAM_M);
-
-    const int tile = blockIdx.x, lane = threadIdx.x;
-    const Tile tl = p.tiles[tile];
-    const int n = tl.count, n_even = (n + 1) & ~1;
-    const long long base = (long long)tile * T;
-
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)n_even * (CAM_M + LMK_M + 9) * 8);
-        bulk_g2s(s_mc, p.msg_cam + base * CAM_M, (uint32_t)n_even * CAM_M * 8, bar);
-        bulk_g2s(s_ml, p.msg_lmk + base * LMK_M, (uint32_t)n_even * LMK_M * 8, bar);
-        bulk_g2s(s_lp, p.linpoint + base * 9, (uint32_t)n_even * 72, bar);
-    }
-    // beliefs are rewritten inside this kernel (after their last reader): plain L2 loads, never the read-only path
-    for (int i = lane; i < CAM_B; i += T) s_cb[i] = __ldcg(p.cam_belief + (long long)tl.cam * CAM_B + i);
-    EdgeRegs r;
-    int lmk = 0;
-    if (lane < n) {
-        lmk = load_edge_scalars(p, base + lane, r);
-        const double2* src = reinterpret_cast<const double2*>(p.lmk_belief + (long long)lmk * LMK_B);
-#pragma unroll
-        for (int k = 0; k < LMK_B / 2; ++k) {
-            const double2 v = __ldcg(src + k);
-            r.bl[2 * k] = v.x;
-            r.bl[2 * k + 1] = v.y;
-        }
-    }
-    __syncwarp();
-    mbar_wait(bar, 0);
-
-    bool relin = false;
-    if (lane < n) relin = edge_sweep<ROBUST>(p, base + lane, r, s_cb, s_lp + lane * 9, s_mc + lane * CAM_M, s_ml + lane * LMK_M);
-    __syncwarp();
-    const unsigned any_relin = __ballot_sync(0xffffffffu, relin);
-
-    // results -> global with ordinary stores (the completion protocol below reasons in the generic proxy only)
-    if (p.stages & ST_MESSAGES) {
-        coop_copy<T>(p.msg_cam + base * CAM_M, s_mc, n * CAM_M);
-        coop_copy<T>(p.msg_lmk + base * LMK_M, s_ml, n * LMK_M);
-    }
-    if (any_relin) coop_copy<T>(p.linpoint + base * 9, s_lp, n * 9);
-    if (lane < CAM_M) {                  // per-tile keyframe sums, rows added in slot order like tile_column_sums<32>
-        double acc = 0.0;
-        for (int q = 0; q < n; ++q) acc += s_mc[q * CAM_M + lane];
-        p.tile_partial[(long long)tile * CAM_M + lane] = acc;
-    }
-    __threadfence();                     // this lane's stores are visible device-wide ...
-    __syncwarp();                        // ... before any lane of the warp announces the tile
-
-    // ---- who is last?
-    int cam_last = 0;
-    if (lane == 0) {
-        const int nt = fp.cam_tile_ptr[tl.cam + 1] - fp.cam_tile_ptr[tl.cam];
-        cam_last = (atomicAdd(fp.cam_done + tl.cam, 1) + 1 == nt) ? 1 : 0;
-        if (cam_last) fp.cam_done[tl.cam] = 0;
-    }
-    cam_last = __shfl_sync(0xffffffffu, cam_last, 0);
-    bool lmk_last = false;
-    if (lane < n) {
-        const int deg = fp.lmk_ptr[lmk + 1] - fp.lmk_ptr[lmk];
-        lmk_last = atomicAdd(fp.lmk_done + lmk, 1) + 1 == deg;
-        if (lmk_last) fp.lmk_done[lmk] = 0;
-    }
-    __threadfence();                     // what the other tiles published before their increments is visible from here on
-    unsigned todo = __ballot_sync(0xffffffffu, lmk_last);
-
-    // ---- landmarks completed by this tile: the whole warp gathers one landmark's message rows at a time
-    //      (lane j takes rows j, j + 32, ... of the CSR list; fixed shuffle tree; same order as belief_kernel<32>)
-    while (todo) {
-        const int src_lane = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int l = __shfl_sync(0xffffffffu, lmk, src_lane);
-        const int p0 = fp.lmk_ptr[l], p1 = fp.lmk_ptr[l + 1];
-        double acc[LMK_M];
-#pragma unroll
-        for (int k = 0; k < LMK_M; ++k) acc[k] = 0.0;
-        for (int q = p0 + lane; q < p1; q += 32) {
-            const double* row = p.msg_lmk + (long long)fp.lmk_slots[q] * LMK_M;
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += __ldcg(row + k);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += fp.lmk_prior[(long long)l * LMK_M + k];
-            double mu[3];
-            spd_solve<3>(acc + 3, acc, mu);
-            double* row = fp.lmk_belief_out + (long long)l * LMK_B;
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) row[k] = acc[k];
-            row[9] = mu[0]; row[10] = mu[1]; row[11] = mu[2];
-            double* m = fp.lmk_mu + (long long)l * 3;
-            m[0] = mu[0]; m[1] = mu[1]; m[2] = mu[2];
-        }
-    }
-    // ---- keyframe completed by this tile: fixed-order sum of its tile partials, prior, 6x6 solve
-    if (cam_last) {
-        const int c = tl.cam;
-        double acc = 0.0;
-        if (lane < CAM_M) {
-            for (int q = fp.cam_tile_ptr[c]; q < fp.cam_tile_ptr[c + 1]; ++q)
-                acc += __ldcg(p.tile_partial + (long long)fp.cam_tiles[q] * CAM_M + lane);
-            fp.cam_partial[(long long)c * CAM_M + lane] = acc;
-            acc += fp.cam_prior[(long long)c * CAM_M + lane];
-        }
-        cam_finalise_row(acc, lane, fp.cam_belief_out + (long long)c * CAM_B, fp.cam_mu + (long long)c * 6);
-    }
-}
 
 // ----------------------------------------------------------------------------------------
 // Peer-memory exchange of the keyframe partial sums (multi-GPU, one process per GPU; opt-in, see gbp_ba_p2p_*).
@@ -1005,8 +439,9 @@ __global__ void __launch_bounds__(32, 12) sweep_fused_kernel(const FusedParams f
 //                             keyframes.  The landmark belief update runs between the two and hides the transfer.
 // No grid-wide or cross-rank barrier: CTA b only depends on CTA b of the other ranks.  Slots and flags are double
 // buffered by epoch parity: a rank can be at most one exchange ahead of the slowest one (it needs everybody's sums of
-// epoch n to finish n), so epoch n + 1 never overwrites data somebody still reads.  A wait gives up after ~2 s and
-// counts a timeout instead of hanging the GPU when a peer died.
+// epoch n to finish n), so epoch n + 1 never overwrites data somebody still reads.  A wait gives up after ~2 s instead of
+// hanging the GPU when a peer died: it counts a timeout (gbp_ba_p2p_status) and the keyframes of that CTA get NaN beliefs,
+// so a lost exchange can never pass as a result.
 // ----------------------------------------------------------------------------------------
 struct P2PHeader {
     unsigned int epoch;      // exchanges completed so far (advanced by the last CTA of the gather kernel)
@@ -1051,6 +486,9 @@ __global__ void __launch_bounds__(128) p2p_gather_update_kernel(const P2PParams 
     volatile P2PHeader* hdr = reinterpret_cast<volatile P2PHeader*>(p.mine);
     const unsigned int epoch = hdr->epoch + 1;
     const int set = (int)(epoch & 1u);
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
+    __syncthreads();
     if ((int)threadIdx.x < p.nranks) {
         const unsigned int* f = p2p_flag(p.mine, p, set, threadIdx.x, blockIdx.x);
         const long long t0 = clock64();
@@ -1060,6 +498,7 @@ __global__ void __launch_bounds__(128) p2p_gather_update_kernel(const P2PParams 
             if (v == epoch) break;
             if (clock64() - t0 > 4000000000LL) {          // ~2 s: a peer is gone; do not hang the GPU
                 atomicAdd(const_cast<unsigned int*>(&hdr->timeouts), 1u);
+                s_timed_out = 1;
                 break;
             }
         }
@@ -1071,6 +510,7 @@ __global__ void __launch_bounds__(128) p2p_gather_update_kernel(const P2PParams 
         if (lane < CAM_M) {
             for (int r = 0; r < p.nranks; ++r) acc += __ldcv(p2p_slot(p.mine, p, set, r, c) + lane);   // rank order
             acc += p.cam_prior[(long long)c * CAM_M + lane];
+            if (s_timed_out) acc = __longlong_as_double(0x7ff8000000000000LL);   // a peer never delivered: poison, do not guess
         }
         cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6);
     }

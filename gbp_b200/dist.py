@@ -8,11 +8,14 @@ ranks exchange those partial sums with ONE all-gather (NCCL over NVLink / NVSwit
 CPU tests); every rank then adds prior + the partials in rank order, so the keyframe beliefs are
 bit-identical everywhere.  ARE / energy need a 3-scalar all-reduce only when the client asks.
 
-Opt-in (`p2p=True` or GBP_P2P=1): the exchange without a collective call.  Every rank writes its partial sums
-straight into the other ranks' exchange buffers over NVLink (CUDA IPC mappings of one small buffer per rank) and
-raises per-CTA flags there; the keyframe update kernel waits on the flags of its own buffer (`gbp_ba_p2p_*`,
-kernels `p2p_scatter_kernel` / `p2p_gather_update_kernel`).  Same rank-ordered sum, so the same bits.  This path
-is built and reviewed but has not had its hardware run yet; the NCCL all-gather stays the default.
+`p2p=True`: the exchange without a collective call.  Every rank writes its partial sums straight into the other
+ranks' exchange buffers over NVLink (CUDA IPC mappings of one small buffer per rank) and raises per-CTA flags
+there; the keyframe update kernel waits on the flags of its own buffer (`gbp_ba_p2p_*`, kernels
+`p2p_scatter_kernel` / `p2p_gather_update_kernel`).  Same rank-ordered sum, so the same bits.
+
+Streams: with world > 1 the engine's kernels and the collective must be ordered on ONE stream.  The graph takes a
+single `torch_stream` (a torch.cuda.Stream; created here when omitted), hands its raw handle to the engine and
+issues the collective under `torch.cuda.stream(torch_stream)`.
 
 The reference has no distributed code; this is new functionality behind the same
 `synchronous_iteration` surface.
@@ -127,6 +130,9 @@ class CudaEngineAdapter:
     def fill_iters(self, v):
         self.eng.fill_iters(v)
 
+    def reset(self):
+        self.eng.reset()
+
     def close(self):
         self.eng.close()
 
@@ -135,14 +141,23 @@ class PartitionedBAGraph:
     """`synchronous_iteration` / `generate_priors_var` / `are` / `energy` over a landmark-partitioned graph."""
 
     def __init__(self, prob: BALProblem, configs, rank=0, world=1, device=0, stream=None, dist=None,
-                 engine_factory=None, torch_stream=None, p2p=None, **engine_kw):
-        engine_kw_stream = torch_stream
-        if p2p is None:
-            import os
-            p2p = os.environ.get("GBP_P2P", "0") not in ("", "0")
+                 engine_factory=None, torch_stream=None, p2p=False, **engine_kw):
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs an initialised torch.distributed module")
+        if engine_factory is None and world > 1:
+            # ONE stream for the engine's kernels and the collective: the raw handle is derived from the torch stream
+            import torch
+            if torch_stream is None:
+                if stream is not None:
+                    raise ValueError("world > 1: pass torch_stream (a torch.cuda.Stream), not a raw stream handle; the "
+                                     "collective has to be ordered on the engine's stream")
+                torch_stream = torch.cuda.Stream(device=device)
+            if stream is not None and int(stream) != int(torch_stream.cuda_stream):
+                raise ValueError("stream and torch_stream name different CUDA streams")
+            stream = torch_stream.cuda_stream
+        engine_kw_stream = torch_stream
         self.rank, self.world, self.dist = rank, world, dist
+        self.n_iterations = 0        # synchronous iterations applied to the state since creation / reset
         self.F_total, self.L_total, self.C = prob.n_edges, prob.n_points, prob.n_keyframes
         sub, self.local_measurements, self.lmk_range = local_problem(prob, rank, world)
         factory = engine_factory or (lambda s, c: CudaEngineAdapter(s, c, device, stream, **engine_kw))
@@ -170,10 +185,19 @@ class PartitionedBAGraph:
             a.landmark_update()         # overlaps the transfer
             a.p2p_gather_update()       # waits on this rank's flags; prior + sums in rank order
             return
-        work = self.dist.all_gather_into_tensor(self._gather, a.partial_tensor(), async_op=True)
-        a.landmark_update()
-        work.wait()
-        a.apply_gathered(self._gather, self.world)
+        with self._stream_ctx():
+            work = self.dist.all_gather_into_tensor(self._gather, a.partial_tensor(), async_op=True)
+            a.landmark_update()
+            work.wait()
+            a.apply_gathered(self._gather, self.world)
+
+    def _stream_ctx(self):
+        """The collective is issued (and waited for) on the engine's stream."""
+        if self._torch_stream is None:
+            import contextlib
+            return contextlib.nullcontext()
+        import torch
+        return torch.cuda.stream(self._torch_stream)
 
     # ------------------------------------------------------------------ API
     def generate_priors_var(self, weaker_factor=100):
@@ -200,6 +224,7 @@ class PartitionedBAGraph:
 
     def synchronous_iteration(self, local_relin=True, robustify=False):
         """gbp/gbp.py:86-92 over the partitioned graph: local sweep -> one all-gather -> keyframe beliefs."""
+        self.n_iterations += 1
         if self.world == 1:
             self.adapter.iterate_single(robustify, local_relin)
             return
@@ -218,7 +243,8 @@ class PartitionedBAGraph:
     def capture(self, local_relin=True, robustify=False):
         """Capture [local sweep -> all-gather -> keyframe update] of one synchronous iteration into a CUDA graph
         (NCCL collectives are capturable), so that an iteration is ONE launch per rank instead of three engine
-        calls plus a Python-side collective.  Needs the torch stream the engine was created on."""
+        calls plus a Python-side collective.  Does NOT advance the state (no iteration is applied): N calls of
+        synchronous_iteration apply N iterations whether or not capture() was called in between."""
         if self.world == 1 or self._torch_stream is None:
             return False
         import torch
@@ -226,9 +252,11 @@ class PartitionedBAGraph:
             ((L.ST_RELIN | L.ST_LOCAL_DAMPING) if local_relin else 0)
         if st in self._graphs:
             return True
-        # one eager iteration first: NCCL sets up its channels outside the capture
-        self.adapter.sweep_local(st)
-        self._exchange_and_update()
+        # NCCL sets up its channels on the first collective, which must happen outside the capture: gather the current
+        # partial sums into the scratch buffer once (touches no state of the solve)
+        if not self.p2p:
+            with self._stream_ctx():
+                self.dist.all_gather_into_tensor(self._gather, self.adapter.partial_tensor())
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._torch_stream, capture_error_mode="thread_local"):
@@ -240,8 +268,14 @@ class PartitionedBAGraph:
     def fill_iters(self, value):
         self.adapter.fill_iters(value)
 
+    def reset(self):
+        """Back to the state right after construction (gbp_ba_reset on every rank): zero messages and priors."""
+        self.adapter.reset()
+        self.n_iterations = 0
+
     def metrics(self):
         """(ARE, energy, number of factors with iters_since_relin == 0) over the WHOLE graph."""
+        self._check_exchange()
         m = self.adapter.metrics()
         if self.world > 1:
             import torch
@@ -256,8 +290,18 @@ class PartitionedBAGraph:
     def energy(self):
         return self.metrics()[1]
 
+    def _check_exchange(self):
+        """A peer-memory exchange that timed out (a peer died or never launched) poisons the keyframe beliefs with NaN on the
+        device; turn it into an exception as soon as the client looks at results."""
+        if self.p2p:
+            done, timeouts = self.adapter.p2p_status()
+            if timeouts:
+                raise RuntimeError(f"rank {self.rank}: {timeouts} peer-memory exchange wait(s) timed out after {done} exchanges; "
+                                   "the keyframe beliefs are invalid")
+
     def get_means(self):
         """All belief means in variable order (keyframes, then landmarks) on every rank."""
+        self._check_exchange()
         cam = self.adapter.cam_means().ravel()
         lmk = self.adapter.lmk_means()
         if self.world > 1:

@@ -55,19 +55,14 @@ typedef struct gbp_config {
     int32_t loss;                /* gbp_loss (gbp/gbp.py:243)                                  */
     int32_t tile_edges;          /* 0 = auto; else 32/64/128 edges per tile (engine tuning)    */
     int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
-    int32_t kernel_variant;      /* 0 = TMA bulk-copy sweep kernel with L2 hints (default; graphs of more than 8192 tiles use
-                                        variant 7 plus a far-ahead L2 prefetch); 1 = first-version LDG kernel; 2 = TMA, no hints;
-                                    3 = 128-register build; 4 = persistent double-buffered (tiles of 32 / 64);
-                                    5 = factor->keyframe messages stored with their rank-2 precision factored (eta[6] | W[2][6],
-                                        Lambda = W^T W: 144 B less traffic per edge and sweep; tiles of 32 / 64).  GBP_F_MSG_CAM
-                                        reads and writes keep the full eta[6] | Lambda[21] form;
-                                    6 = early issue: bulk loads, scalars and the landmark gather do not wait for the tile descriptor;
-                                    7 = 5 + 6; 8 / 9 = 7 / 6 compiled for 7 CTAs per SM (experiments);
-                                    10 = warp-specialised persistent ring (experiment, producer-bound: 2x slower);
-                                    11 = one-kernel iteration for small graphs (sweep + belief update in one launch through
-                                         per-variable completion counters; gbp_ba_iterate only; NOT yet run on hardware);
-                                    12 = 7 with the per-tile keyframe sums formed in registers (shuffle reduce-scatter) instead of through
-                                         full-form rows in shared memory, L2 prefetch on large graphs; NOT yet run on hardware */
+    int32_t kernel_variant;      /* build of the sweep kernel: 0 = automatic (graphs of up to 8192 tiles live in L2 and get build 1,
+                                    larger ones stream from HBM and get build 2);
+                                    1 = full 27-double factor->keyframe message rows, bulk copies sized by the tile descriptor;
+                                    2 = streaming build: factor->keyframe messages stored with their rank-2 precision factored
+                                        (eta[6] | W[2][6], Lambda = W^T W: 144 B less traffic per edge and sweep), nothing in the
+                                        prologue waits for the tile descriptor, far-ahead L2 prefetch on graphs of more than 8192
+                                        tiles; tiles of 32 / 64.  GBP_F_MSG_CAM reads and writes keep the full eta[6] | Lambda[21]
+                                        form.  Both builds run the same per-edge arithmetic (gbp_edge.cuh). */
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */
@@ -120,6 +115,14 @@ int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F,
                   const double* cam_mu0 /* C x 6 */, const double* lmk_mu0 /* L x 3 */,
                   const double K[4] /* fx fy cx cy */, int device, void* stream, gbp_handle* out);
 int gbp_ba_destroy(gbp_handle h);
+/* Shell cache (no reference counterpart).  gbp_ba_destroy does not return the graph's device arena, its page-locked
+ * staging block and its instantiated CUDA graphs to the driver: the next gbp_ba_create on the same device reuses the
+ * arena when it is large enough, and the CUDA graphs too when the new graph has the same shape and parameters (ba.py
+ * run file after file: no cudaMalloc / cudaFree / cudaGraphInstantiate per problem).  gbp_cache_configure bounds it
+ * (defaults: 4 shells, arenas of at most 1 GiB; 0 shells = off, frees everything cached now); gbp_cache_stats:
+ * out = {creates, arena reuses, graph reuses, shells evicted, shells cached now, bytes cached now}. */
+int gbp_cache_configure(int32_t max_shells, int64_t max_arena_bytes);
+int gbp_cache_stats(int64_t out[6]);
 /* Back to the state right after gbp_ba_create (zero messages and priors, initial means and
  * linearisation points, iters_since_relin = 1): re-run a solve without rebuilding the graph. */
 int gbp_ba_reset(gbp_handle h);
@@ -142,7 +145,7 @@ void gbp_plan_destroy(gbp_plan p);
 
 /* Engine layout chosen for this graph (no reference counterpart; used by bench.py to count the bytes a sweep moves):
  * out[0] doubles per stored factor->keyframe message (27 full, 18 factored), out[1] L2 prefetch distance in tiles,
- * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice), out[3] programmatic launches. */
+ * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice: 1 or 2), out[3] reserved (0). */
 int gbp_ba_layout(gbp_handle h, int64_t out[4]);
 
 /* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
@@ -179,8 +182,8 @@ int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks);
  *   per iteration:     gbp_ba_sweep_local(h, stages | GBP_STAGE_DEFER_LANDMARKS); gbp_ba_p2p_scatter(h);
  *                      gbp_ba_landmark_update(h);  gbp_ba_p2p_gather_update(h);
  *   gbp_ba_p2p_status  out[0] = exchanges completed, out[1] = waits that timed out (~2 s; a peer is gone).
- * Every rank must destroy its handle only after all ranks stopped iterating (barrier on the host side).
- * Status of this path: built and reviewed, NOT yet run on hardware (round 2). */
+ * A wait that times out also poisons the keyframe beliefs of its CTA with NaN: a lost exchange never passes as a result.
+ * Every rank must destroy its handle only after all ranks stopped iterating (barrier on the host side). */
 #define GBP_IPC_HANDLE_BYTES 64
 int gbp_ba_p2p_init(gbp_handle h, int rank, int nranks, void* ipc_handle_out);
 int gbp_ba_p2p_attach(gbp_handle h, const void* ipc_handles);

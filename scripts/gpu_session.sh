@@ -1,12 +1,17 @@
 #!/bin/bash
 # One GPU-box session.  Every step has its own timeout and writes under gpurun_out/ so a cut-off call still leaves
-# what finished.  STEPS selects: tests exp ab bench (default: all four).
+# what finished.  STEPS selects: tests bench bench2 tests2 (default: tests bench).  TAG names the output files.
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-STEPS=${STEPS:-"tests exp ab bench"}
+STEPS=${STEPS:-"tests bench"}
+TAG=${TAG:-r2}
 for s in $STEPS; do case $s in
-tests) echo "== default gpu suite"; timeout 400 python -m pytest tests -m gpu -x -q --no-header -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/gpu_tests.log;;
-exp) echo "== experimental tests"; GBP_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_variants_gpu.py -q --no-header -p no:cacheprovider > gpurun_out/exp_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/exp_tests.log;;
-ab) echo "== ab_variants" ; timeout 300 python scripts/ab_variants.py $AB_ARGS > gpurun_out/ab_stdout.log 2> gpurun_out/ab_stderr.log; echo "rc=$?"; cut -c1-700 gpurun_out/ab_stdout.log; tail -5 gpurun_out/ab_stderr.log;;
-bench) echo "== bench"; GBP_BENCH_DEBUG=1 timeout 280 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_stderr.log; echo "rc=$?"; cut -c1-3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_stderr.log;;
+tests) echo "== default gpu suite"; timeout 900 python -m pytest tests -m gpu -x -q --no-header -p no:cacheprovider ${PYTEST_ARGS} > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/${TAG}_gpu_tests.log;;
+bench) echo "== bench"; GBP_BENCH_DEBUG=1 timeout 600 python bench.py ${BENCH_ARGS} > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "rc=$?"; cut -c1-6000 gpurun_out/${TAG}_bench_n1.json; tail -45 gpurun_out/${TAG}_bench_n1.err;;
+refarm) echo "== bench --impl reference"; timeout 600 python bench.py --impl reference ${BENCH_ARGS} > gpurun_out/${TAG}_bench_ref_n1.json 2> gpurun_out/${TAG}_bench_ref_n1.err; echo "rc=$?"; cut -c1-2000 gpurun_out/${TAG}_bench_ref_n1.json;;
+tests2) echo "== 2-GPU partition tests (NCCL and peer-memory exchange)"; timeout 400 python -m pytest tests/test_dist_gpu.py -q -x --no-header -p no:cacheprovider > gpurun_out/${TAG}_dist_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/${TAG}_dist_tests.log;;
+benchN) N=${NGPU:-2}; for x in "" "--p2p"; do
+    echo "== bench --gpus $N $x"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N ${BENCH_ARGS} $x > gpurun_out/${TAG}_bench_n${N}${x}.json 2> gpurun_out/${TAG}_bench_n${N}${x}.err; echo "rc=$?"
+    cut -c1-5000 gpurun_out/${TAG}_bench_n${N}${x}.json; tail -8 gpurun_out/${TAG}_bench_n${N}${x}.err
+  done;;
 esac; done

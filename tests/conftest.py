@@ -38,8 +38,21 @@ def golden_problem(G):
 
 
 def relerr(a, b):
+    """max |a - b| / max |b| over the WHOLE table (a table-level norm: small entries are measured against the largest one;
+    use relerr_rows where every variable has to be right on its own scale)."""
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def relerr_rows(a, b):
+    """Per-variable relative error: max over rows v of ||a_v - b_v||_2 / ||b_v||_2 (Frobenius norm for matrix rows)."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    den = np.maximum(np.linalg.norm(b, axis=1), 1e-300)
+    return float(np.max(np.linalg.norm(a - b, axis=1) / den))
+
+
+REF_COPY = os.path.join(ROOT, "baseline", "_ref")
 
 
 @pytest.fixture(scope="session")

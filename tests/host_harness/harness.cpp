@@ -234,76 +234,6 @@ void hs_sweep(void* hv, int stages) {
     if (stages & ST_BELIEFS) h->beliefs();
 }
 
-// The schedule of the one-kernel iteration (sweep_fused_kernel, kernel_variant 11) replayed sequentially: tiles (runs of
-// <= T consecutive edges of one keyframe) are swept in a RANDOM order, and a variable's belief is rewritten the moment its
-// last edge (last tile) has been swept -- while other tiles are still to come.  If any later tile read a rewritten belief
-// the trajectory would leave the reference's; it must stay bit-identical to hs_iterate (same summation orders).
-void hs_iterate_fused_schedule(void* hv, int n_iters, int robustify, int local_relin, int T, unsigned seed) {
-    HostSweep* h = static_cast<HostSweep*>(hv);
-    if (h->factored) return;                       // the device kernel exists for full-form rows only
-    const int st = iteration_stages(robustify, local_relin);
-    // tiles over the factor order (camera-major): [begin, end) of one keyframe, at most T edges
-    std::vector<std::pair<long, long>> tiles;
-    for (long e = 0; e < h->F;) {
-        long end = e + 1;
-        while (end < h->F && end - e < T && h->cam[end] == h->cam[e]) ++end;
-        tiles.push_back({e, end});
-        e = end;
-    }
-    std::vector<int> cam_tiles(h->C, 0), lmk_deg(h->L, 0);
-    for (auto& t : tiles) cam_tiles[h->cam[t.first]]++;
-    for (long e = 0; e < h->F; ++e) lmk_deg[h->lmk[e]]++;
-    std::vector<std::vector<long>> lmk_edges(h->L), cam_edges(h->C);
-    for (long e = 0; e < h->F; ++e) { lmk_edges[h->lmk[e]].push_back(e); cam_edges[h->cam[e]].push_back(e); }
-    unsigned long long rng = seed * 2862933555777941757ULL + 3037000493ULL;
-    std::vector<size_t> order(tiles.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::vector<int> cam_done(h->C), lmk_done(h->L);
-    for (int it = 0; it < n_iters; ++it) {
-        for (size_t i = order.size(); i > 1; --i) {          // Fisher-Yates with a 64-bit LCG
-            rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
-            std::swap(order[i - 1], order[(size_t)((rng >> 33) % i)]);
-        }
-        std::fill(cam_done.begin(), cam_done.end(), 0);
-        std::fill(lmk_done.begin(), lmk_done.end(), 0);
-        SweepParams p = h->prm;
-        p.stages = st;
-        p.linpoint = h->linpoint.data(); p.msg_cam = h->msg_cam.data(); p.msg_lmk = h->msg_lmk.data();
-        p.iters = h->iters.data(); p.flags = h->flags.data(); p.sigma2a = h->sigma2a.data();
-        for (size_t oi = 0; oi < order.size(); ++oi) {
-            const auto t = tiles[order[oi]];
-            const int c = h->cam[t.first];
-            for (long e = t.first; e < t.second; ++e) {       // the tile's sweep, beliefs as they are in memory NOW
-                EdgeRegs r;
-                r.it = h->iters[e]; r.fl = h->flags[e];
-                r.var = h->robust ? h->sigma2a[e] : p.var0;
-                r.z[0] = h->z[2 * e]; r.z[1] = h->z[2 * e + 1];
-                for (int k = 0; k < LMK_B; ++k) r.bl[k] = h->lmk_belief[(size_t)h->lmk[e] * LMK_B + k];
-                const double* cb = &h->cam_belief[(size_t)c * CAM_B];
-                double *lp = &h->linpoint[9 * e], *ml = &h->msg_lmk[(size_t)LMK_M * e], *mc = &h->msg_cam[(size_t)CAM_M * e];
-                if (h->robust) edge_sweep<true>(p, e, r, cb, lp, mc, ml);
-                else edge_sweep<false>(p, e, r, cb, lp, mc, ml);
-            }
-            for (long e = t.first; e < t.second; ++e) {       // landmarks whose last edge this was
-                const int l = h->lmk[e];
-                if (++lmk_done[l] != lmk_deg[l]) continue;
-                double acc[LMK_M] = {0};
-                for (long f : lmk_edges[l]) for (int k = 0; k < LMK_M; ++k) acc[k] += h->msg_lmk[(size_t)LMK_M * f + k];
-                double* row = &h->lmk_belief[(size_t)l * LMK_B];
-                for (int k = 0; k < LMK_M; ++k) row[k] = acc[k] + h->lmk_prior[(size_t)l * LMK_M + k];
-                spd_solve<3>(row + 3, row, row + 9);
-            }
-            if (++cam_done[c] == cam_tiles[c]) {              // keyframe whose last tile this was
-                double acc[CAM_M] = {0};
-                for (long f : cam_edges[c]) for (int k = 0; k < CAM_M; ++k) acc[k] += h->msg_cam[(size_t)CAM_M * f + k];
-                double* row = &h->cam_belief[(size_t)c * CAM_B];
-                for (int k = 0; k < CAM_M; ++k) row[k] = acc[k] + h->cam_prior[(size_t)c * CAM_M + k];
-                spd_solve<6>(row + 6, row, row + 27);
-            }
-        }
-    }
-}
-
 void hs_fill_iters(void* hv, int v) {
     HostSweep* h = static_cast<HostSweep*>(hv);
     std::fill(h->iters.begin(), h->iters.end(), v);

@@ -3,7 +3,7 @@ inputs and against the fixtures generated from the unmodified reference."""
 import numpy as np
 import pytest
 
-from conftest import golden_configs, golden_problem, load_golden, relerr
+from conftest import golden_configs, golden_problem, load_golden, relerr, relerr_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -151,9 +151,21 @@ def test_fr1desk_200_iterations_converged_beliefs():
     assert sorted(seen) == [0, 15, 16, 99, 199]
     assert abs(are[-1] - 1.656861417438452) < 1e-6 and abs(en[-1] - 7128.308364695148) < 1e-2
     assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
-    assert np.max(np.abs(nrel - G["n_relin"])) <= 2, np.abs(nrel - G["n_relin"]).max()   # branch decisions
+    # relinearisation is a threshold decision (|linpoint - mu| > beta) on a chaotic trajectory: a factor whose distance sits within
+    # rounding of beta may flip one iteration earlier / later than in the reference.  Bound both the size and the number of such reads.
+    dn = np.abs(nrel - G["n_relin"])
+    assert dn.max() <= 2 and int((dn > 0).sum()) <= 10, (dn.max(), int((dn > 0).sum()), np.nonzero(dn)[0][:20])
     # all factors relinearise in sweep 15 (seen by the client at the start of outer iteration 16)
     assert nrel[16] == 13298 and nrel[:16].sum() == 0
+    # north-star gate PER VARIABLE (not only over the whole table): every keyframe's / landmark's converged mean and
+    # precision block within 1e-4 relative of the reference in its own norm: ||dmu_v|| / ||mu_v||, ||dLam_v||_F / ||Lam_v||_F
+    from gbp_b200 import _lib as L
+    ce, cl, cm = _unpack(graph._eng.read(L.F_CAM_BELIEF), 6)
+    le, ll, lm = _unpack(graph._eng.read(L.F_LMK_BELIEF), 3)
+    per_var = {"cam_mu": relerr_rows(cm, G["s199_cam_mu"].reshape(-1, 6)), "lmk_mu": relerr_rows(lm, G["s199_lmk_mu"].reshape(-1, 3)),
+               "cam_lam": relerr_rows(cl, G["s199_cam_lam"].reshape(-1, 36)), "lmk_lam": relerr_rows(ll, G["s199_lmk_lam"].reshape(-1, 9)),
+               "cam_eta": relerr_rows(ce, G["s199_cam_eta"].reshape(-1, 6)), "lmk_eta": relerr_rows(le, G["s199_lmk_eta"].reshape(-1, 3))}
+    assert all(v < TOL_CONVERGED for v in per_var.values()), per_var
     graph.close()
 
 
@@ -177,24 +189,21 @@ def test_tiling_and_landmark_blocking_do_not_change_results(tile, block):
 
 
 def test_kernel_variants_agree():
-    """The TMA bulk-copy sweep kernel and the first-version LDG kernel are the same arithmetic."""
+    """Tile size does not change the results beyond summation order; the streaming build (factored keyframe messages)
+    agrees with the full-row build to rounding."""
     from gbp_b200.ba import create_ba_graph
     from gbp_b200 import _lib as L
     G = load_golden("fr1desk_vsmall_huber")
     gs = [create_ba_graph(golden_problem(G), golden_configs(G), tile_edges=t, kernel_variant=v)
-          for t, v in ((64, 0), (64, 1), (128, 0), (64, 2), (64, 3), (64, 4), (32, 4))]
+          for t, v in ((64, 1), (64, 0), (128, 1), (32, 1), (64, 2), (32, 2))]
     for g in gs:
         g.generate_priors_var(50.0)
         g.update_all_beliefs()
         g.iterate(8); g._eng.fill_iters(8); g.iterate(12, robustify=True)
     for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ADAPTIVE_VAR, L.F_ITERS, L.F_FLAGS):
-        for k in (1, 3, 4, 5):      # same tile size: same arithmetic in the same order (variant 3 may contract differently)
-            if k == 4:
-                assert relerr(gs[k]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, (f, k)
-            else:
-                assert np.array_equal(gs[0]._eng.read(f), gs[k]._eng.read(f)), (f, k)
-        assert relerr(gs[2]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, f
-        assert relerr(gs[6]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, f
+        assert np.array_equal(gs[0]._eng.read(f), gs[1]._eng.read(f)), f     # automatic choice on a small graph = build 1
+        for k in (2, 3, 4, 5):
+            assert relerr(gs[k]._eng.read(f), gs[0]._eng.read(f)) < 1e-9, (f, k)
     for g in gs:
         g.close()
 
@@ -340,26 +349,73 @@ def test_error_behaviour():
     g.close()
 
 
-def test_client_script_trace(tmp_path, capsys):
-    """examples/ba_client.py (the call sequence and printed trace of ba.py:48-105, including the Python loops over
-    graph.factors) on fr1desk_vsmall read from a BAL text file, against the reference's trace."""
-    import importlib.util
-    from gbp_b200 import balio
-    from conftest import ROOT
+def _run_reference_script(script, args, timeout=600):
+    """Run an UNMODIFIED script of the staged reference copy (baseline/_ref, put there by __graft_entry__.build()) against
+    this engine: `python -m gbp_b200.run <script> ...` only puts gbp_b200/compat (packages gbp / utils / vis) first on sys.path."""
     import os
-    G = load_golden("fr1desk_vsmall")
-    path = str(tmp_path / "fr1desk_vsmall.txt")
-    balio.write_bal(path, golden_problem(G), ["fr1desk_vsmall (from the fixture)"])
-    spec = importlib.util.spec_from_file_location("ba_client", os.path.join(ROOT, "examples", "ba_client.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    graph, trace = mod.main(["--bal_file", path, "--n_iters", "20"])
-    trace = np.array(trace)
-    assert relerr(trace[:, 0], G["are"][:20]) < 1e-6 and relerr(trace[:, 1], G["energy"][:20]) < 1e-6   # same tolerance as the trajectory tests
-    assert np.array_equal(trace[:, 2].astype(int), G["n_relin"][:20])
-    out = capsys.readouterr().out
-    assert "Number of keyframes: 10" in out and "Iteration 16 // ARE 23.6383" in out
-    graph.close()
+    import subprocess
+    import sys
+    from conftest import REF_COPY, ROOT
+    path = os.path.join(REF_COPY, script)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: __graft_entry__.build() stages the reference copy (it ships to the GPU box with the tree)")
+    import hashlib
+    res = subprocess.run([sys.executable, "-m", "gbp_b200.run", path] + args, cwd=REF_COPY, env=dict(os.environ, PYTHONPATH=ROOT),
+                         capture_output=True, text=True, timeout=timeout)
+    assert res.returncode == 0, res.stderr[-2000:]
+    return res.stdout, hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def _parse_ba_trace(out):
+    import re
+    rows = re.findall(r"Iteration (\d+) // ARE ([-+0-9.eE]+|nan|inf) // Energy ([-+0-9.eE]+|nan|inf) // Num factors relinearising (\d+)", out)
+    return np.array([[float(x) for x in r] for r in rows])
+
+
+# sha256 of /root/reference/ba.py at the survey commit (5670a49): the script the test runs must be the reference's own bytes
+BA_PY_SHA256 = "ab5d4ac0748cadc8f562fa0e2e3be6a614664166effe66c6721f568e1fe7df86"
+
+
+@pytest.mark.parametrize("data,fixture,extra", [
+    ("fr1desk_vsmall.txt", "fr1desk_vsmall", []),
+    ("fr1desk_vsmall.txt", "fr1desk_vsmall_huber", ["--loss", "huber"]),
+    ("fr1desk_vsmall.txt", "fr1desk_vsmall_constant", ["--loss", "constant"]),
+    ("fr1desk_vsmall.txt", "fr1desk_vsmall_float", ["--float_implementation"]),
+    ("fr1desk.txt", "fr1desk", []),
+])
+def test_unmodified_reference_ba_py(data, fixture, extra):
+    """BASELINE configs 2 / 3 as the north star states them: the reference's own ba.py, unmodified (`import vis`, the Python
+    loops over graph.factors, viewer.update), runs on the GPU engine and prints the reference's trace to the printed digits
+    (ba.py:68-105; ARE / energy to 4 decimals, relinearisation counts exactly on vsmall, within the branch-decision
+    bound of the converged-belief test on fr1desk)."""
+    G = load_golden(fixture)
+    n_iters = int(G["n_iters"])
+    out, sha = _run_reference_script("ba.py", ["--bal_file", f"data/{data}", "--n_iters", str(n_iters)] + extra)
+    assert sha == BA_PY_SHA256
+    C, Lm, F = len(G["in_cam0"]), len(G["in_lmk0"]), len(G["in_cam_id"])
+    assert f"Number of keyframes: {C}" in out and f"Number of landmarks: {Lm}" in out and f"Number of measurement factors: {F}" in out
+    tr = _parse_ba_trace(out)
+    assert tr.shape == (n_iters, 4) and np.array_equal(tr[:, 0], np.arange(n_iters))
+    float_impl = bool(G["float_impl"])
+    tol = 1e-3 if float_impl else 1e-6         # the worse-conditioned float trace: see tests/test_math_host.py
+    ref_are, ref_en = G["are"][:n_iters], G["energy"][:n_iters]
+    assert np.all(np.abs(tr[:, 1] - ref_are) <= 0.5e-4 + tol * np.abs(ref_are))      # printed with 4 decimals
+    assert np.all(np.abs(tr[:, 2] - ref_en) <= 0.5e-4 + tol * np.abs(ref_en))
+    dn = np.abs(tr[:, 3].astype(int) - G["n_relin"][:n_iters])
+    assert dn.max() <= (2 if fixture == "fr1desk" else 0), np.nonzero(dn)[0]
+    if float_impl:
+        assert out.count("Weakening priors") == 5
+
+
+def test_unmodified_reference_ndim_posegraph():
+    """BASELINE config 1: ndim_posegraph.py of the staged reference copy, unmodified, on the host graph classes (CPU by
+    contract) -- the check of tests/test_hostgraph.py, here from the shipped copy on the box."""
+    G = load_golden("posegraph_n50_d3")
+    out, _ = _run_reference_script("ndim_posegraph.py", ["--n_varnodes", "50", "--dim", "3"])
+    lines = [l for l in out.splitlines() if l.startswith("Iteration")]
+    assert len(lines) == 50
+    assert [float(l.split("Energy")[1].split("//")[0]) for l in lines] == G["energy"].tolist()
+    assert [float(l.split("MAP")[1]) for l in lines] == G["dist"].tolist()
 
 
 def test_snapshot_paths_agree():
@@ -433,7 +489,7 @@ def test_full_size_properties():
     assert set(np.unique(its).tolist()) <= {0, 1, 2, 3, 4, 13} and (its == 4).mean() > 0.9
     assert np.isfinite(cb).all() and np.isfinite(lb).all() and np.isfinite(mc).all()
     # (5) storage order (tiles, landmark blocks) and kernel variant do not change the state
-    h = create_ba_graph(prob, cfg, tile_edges=128, lmk_block=50_000, kernel_variant=2)
+    h = create_ba_graph(prob, cfg, tile_edges=128, lmk_block=50_000, kernel_variant=1)
     h.generate_priors_var(50.0)
     h.update_all_beliefs()
     h.iterate(12, robustify=True, local_relin=True)

@@ -21,6 +21,9 @@ def test_reference_arm_json_line():
     assert d["metric"] == "gbp_messages_per_sec" and d["unit"] == "msgs/s" and d["higher_is_better"] is True
     assert d["steps"] == 1 and d["warmup"] == 0 and d["vs_baseline"] is None and d["dtype"] == "f64"
     assert "fr1desk" in d["config"]["workload"] and d["config"]["msgs_per_step"] == 200 * 2 * 13298
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(1, 1000, 1_000_000)       # both arms print the same config object
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -43,8 +46,25 @@ def test_stdout_carries_only_the_json_line():
     assert res.stdout == '{"ok": 1}\n' and "NCCL version" in res.stderr and "python-level noise" in res.stderr
 
 
+def test_reference_arm_multi_gpu_line_matches_our_config():
+    """N > 1: rank 0 times the C port on a bounded sample of the partitioned synthetic workload and prints OUR arm's config."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                          "--synth-cams", "100", "--synth-lmks", "20000"], capture_output=True, text=True, check=True, cwd=ROOT, env=env,
+                         timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong"
+    assert d["config"] == bench.bench_config(2, 100, 20000) and "partitioned over 2 GPUs" in d["config"]["workload"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 1e5 and d["e2e"]["value"] == d["value"]
+
+
 def test_roofline_entry_counts_both_byte_figures():
-    """`achieved` = SURVEY 8(d) bytes / launch time (the contract); the factored layout's own bytes are reported beside it."""
+    """`achieved` / `frac` = the bytes the layout in use has to move / launch time (what the HBM delivers); SURVEY 8(d)'s
+    layout-independent 696 B per factor is reported beside it as *_survey_bytes."""
     sys.path.insert(0, ROOT)
     import bench
     F, L, C = 10_000_000, 1_000_000, 1000
@@ -53,16 +73,17 @@ def test_roofline_entry_counts_both_byte_figures():
     assert survey == 696 * F + 96 * L + 264 * C and moved == 552 * F + 96 * L + 264 * C
     r = bench.roofline_entry("w", 1.0, survey, moved, 6547.8, 5_599_662_000, 18)
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6547.8
-    assert abs(r["achieved"] - survey / 1e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6547.8) < 1e-12
-    assert abs(r["achieved_moved"] - moved / 1e-3 / 1e9) < 1e-6 and r["frac_moved"] < r["frac"]
+    assert abs(r["achieved"] - moved / 1e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6547.8) < 1e-12
+    assert abs(r["achieved_survey_bytes"] - survey / 1e-3 / 1e9) < 1e-6 and r["frac"] < r["frac_survey_bytes"]
+    assert r["algorithmic_bytes_per_launch"] == moved and r["survey_bytes_per_launch"] == survey
     assert r["traffic"] == 5_599_662_000 and r["ms_per_launch"] == 1.0 and "552" in r["bytes_note"]
     full = bench.roofline_entry("w", 1.2, survey, survey, 6547.8, None, 27)
-    assert full["achieved"] == full["achieved_moved"] and full["traffic"] is None
+    assert full["achieved"] == full["achieved_survey_bytes"] and full["traffic"] is None
     json.dumps(r)
 
 
 def test_synthetic_section_builds_its_json_with_a_stub_engine(monkeypatch):
-    """bench_synthetic's bookkeeping (byte counts, roofline object, JSON-serialisable output) with the GPU engine, torch
+    """bench_synthetic_1gpu's bookkeeping (byte counts, roofline object, JSON-serialisable output) with the GPU engine, torch
     and the generator replaced by stubs: a typo there would cost the round its bench line."""
     import types
     sys.path.insert(0, ROOT)
@@ -71,38 +92,35 @@ def test_synthetic_section_builds_its_json_with_a_stub_engine(monkeypatch):
     import gbp_b200.synthetic as gsyn
 
     class Ev:
-        def __init__(self, enable_timing=True): pass
         def record(self): pass
         def elapsed_time(self, other): return 24.0
 
-    torch = types.SimpleNamespace(cuda=types.SimpleNamespace(Event=Ev, current_stream=lambda: None, synchronize=lambda: None))
-
     class Eng:
         F, L, C, n_tiles, tile_edges = 10_000_000, 1_000_000, 1000, 158239, 64
-        msg_cam_width, sweep_variant, prefetch_tiles = 18, 7, 600
+        msg_cam_width, sweep_variant, prefetch_tiles = 18, 2, 600
         def launch_count(self): return 0
         def time_iterations(self, k, r, l, per_kernel=False): return 1.2 * k, 1.0 * k
 
     class PG:
         p2p = False
+        n_iterations = 223
         def __init__(self, *a, **kw): self.engine = Eng()
         def generate_priors_var(self, w): pass
         def update_all_beliefs(self): pass
-        def capture(self, **kw): return False
         def synchronous_iteration(self, **kw): pass
         def metrics(self): return 2.3, 8.5e6, 0
         def close(self): pass
 
     monkeypatch.setattr(gdist, "PartitionedBAGraph", PG)
     monkeypatch.setattr(gsyn, "make_synthetic", lambda c, l, o, seed=0: types.SimpleNamespace(n_edges=10_000_000, n_points=1_000_000, n_keyframes=1000))
-    args = types.SimpleNamespace(synth_cams=1000, synth_lmks=1_000_000, p2p=False, no_capture=False, synth_iters=20, warmup=3, synth_sustained=200)
-    synth, roof = bench.bench_synthetic(args, torch, None, 0, 1, 0, 1, 6547.8, lambda: None, lambda x: x)
+    args = types.SimpleNamespace(synth_cams=1000, synth_lmks=1_000_000, synth_iters=20, warmup=3, synth_sustained=200)
+    ctx = types.SimpleNamespace(torch=types.SimpleNamespace(cuda=types.SimpleNamespace(synchronize=lambda: None)), local=0, stream=1,
+                                hbm_peak=6547.8, events=lambda: (Ev(), Ev()))
+    synth, roof = bench.bench_synthetic_1gpu(ctx, args)
     json.dumps({"synthetic": synth, "roofline": roof})
-    assert abs(synth["ms_per_iteration"] - 1.2) < 1e-9 and synth["layout"]["msg_cam_doubles"] == 18 and synth["exchange"] is None
-    assert abs(roof["ms_per_launch"] - 1.0) < 1e-12 and roof["frac"] > 1.0 > roof["frac_moved"] > 0.8
+    assert abs(synth["ms_per_iteration"] - 1.2) < 1e-9 and synth["layout"]["msg_cam_doubles"] == 18
+    assert abs(roof["ms_per_launch"] - 1.0) < 1e-12 and roof["frac_survey_bytes"] > 1.0 > roof["frac"] > 0.8
     assert roof["traffic"] == json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["sweep_kernel/synthetic_1000_1000000_10000000"]["bytes"]
-    synth2, roof2 = bench.bench_synthetic(args, torch, None, 0, 2, 0, 1, 6547.8, lambda: None, lambda x: x)
-    assert roof2 is None and "NCCL" in synth2["exchange"] and "2 GPUs" in synth2["workload"]
 
 
 def test_build_entry_point():

@@ -36,19 +36,17 @@ def _worker(rank, world, port, out_dir, p2p=False):
             pg.fill_iters(1)
         trace.append(pg.metrics())
         if i == 12:
-            assert pg.capture(local_relin=True, robustify=True)   # capture() itself runs one eager iteration
-        else:
-            pg.synchronous_iteration(robustify=True, local_relin=True)
+            assert pg.capture(local_relin=True, robustify=True)   # from here on an iteration is one graph replay; no state change
+        pg.synchronous_iteration(robustify=True, local_relin=True)
     trace.append(pg.metrics())
     status = pg.adapter.p2p_status() if p2p else (0, 0)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace), p2p_status=np.array(status))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace), p2p_status=np.array(status),
+             n_iterations=pg.n_iterations)
     pg.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, pytest.param(True, marks=pytest.mark.skipif(
-    os.environ.get("GBP_TEST_EXPERIMENTAL", "0") in ("", "0"),
-    reason="peer-memory exchange kernels: not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1"))], ids=["nccl", "p2p"])
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl", "p2p"])
 def test_two_gpu_partition_matches_single_gpu(tmp_path, p2p):
     import torch
     if torch.cuda.device_count() < 2:
@@ -62,8 +60,9 @@ def test_two_gpu_partition_matches_single_gpu(tmp_path, p2p):
     mp.spawn(_worker, args=(2, port, str(tmp_path), p2p), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     assert np.array_equal(r0["means"], r1["means"]) and np.array_equal(r0["trace"], r1["trace"])
-    if p2p:      # one exchange per belief update (1 initial + 25 iterations + capture's eager one), no wait timed out
-        assert r0["p2p_status"][0] >= 26 and r0["p2p_status"][1] == 0 and r1["p2p_status"][1] == 0
+    assert int(r0["n_iterations"]) == 25
+    if p2p:      # one exchange per belief update (1 initial + 25 iterations), no wait timed out
+        assert r0["p2p_status"][0] == 26 and r0["p2p_status"][1] == 0 and r1["p2p_status"][1] == 0
     prob = make_synthetic(40, 6000, 8, seed=5)
     pg = PartitionedBAGraph(prob, CFG)
     pg.generate_priors_var(50.0)

@@ -43,7 +43,6 @@ def hh():
     lib.hs_update_beliefs.argtypes = [vp]
     lib.hs_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.hs_fill_iters.argtypes = lib.hs_sweep.argtypes = [vp, C.c_int]
-    lib.hs_iterate_fused_schedule.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
     lib.hs_metrics.argtypes = [vp, vp]
     lib.hs_read.argtypes = lib.hs_read_int.argtypes = [vp, C.c_int, vp]
     lib.hs_set_factored.argtypes = [vp, C.c_int]
@@ -335,30 +334,4 @@ def test_staged_calls_equal_one_sweep(hh, factored):
         assert relerr(b.read(field, rows, w), a.read(field, rows, w)) < 1e-12, field
     assert np.array_equal(a.read_int(7), b.read_int(7)) and np.array_equal(a.read_int(8), b.read_int(8))
     assert (a.read_int(7) < 17).any()
-    a.close(); b.close()
-
-
-@pytest.mark.parametrize("name,tile", [("fr1desk_vsmall_huber", 32), ("fr1desk_vsmall", 7), ("fr1desk", 32)])
-def test_one_kernel_iteration_schedule_keeps_the_jacobi_semantics(hh, name, tile):
-    """The schedule of kernel_variant 11 (sweep_fused_kernel): tiles swept in a random order, every variable's belief
-    rewritten as soon as its last edge / tile has been swept.  synchronous_iteration (gbp/gbp.py:86-92) computes all
-    messages of a sweep from the beliefs of the previous one; the schedule keeps that because the readers of a belief are
-    exactly the edges that must finish first -- so the state must stay BIT-identical to the two-phase iteration, for
-    any order, through relinearisations and robust reweighting."""
-    G = load_golden(name)
-    cfg = golden_configs(G)
-    a, b = HostSweep(hh, G, cfg), HostSweep(hh, G, cfg)
-    for s in (a, b):
-        hh.hs_generate_priors(s.h, cfg["prior_std_weaker_factor"])
-        hh.hs_update_beliefs(s.h)
-    n = min(int(G["n_iters"]), 40)
-    for i in range(n):
-        if i in (3, 8):
-            hh.hs_fill_iters(a.h, 1); hh.hs_fill_iters(b.h, 1)
-        hh.hs_iterate(a.h, 1, 1, 1)
-        hh.hs_iterate_fused_schedule(b.h, 1, 1, 1, tile, 1234 + i)
-    for field, rows, w in ((0, a.C, 33), (1, a.L, 12), (4, a.F, 27), (5, a.F, 9), (6, a.F, 9), (9, a.F, 1)):
-        assert np.array_equal(a.read(field, rows, w), b.read(field, rows, w)), field
-    assert np.array_equal(a.read_int(7), b.read_int(7)) and np.array_equal(a.read_int(8), b.read_int(8))
-    assert (a.read_int(7) < n).any()            # relinearisations happened on the way
     a.close(); b.close()

@@ -1,26 +1,22 @@
-"""GPU parity of the engine variants: the factored keyframe-message layout (kernel_variants 5 / 7 / 8; what large graphs
-use by default), the early-issue builds (6 / 9) and programmatic dependent launches (GBP_PDL=1), forced onto the small
-fixture graphs so that every checkpoint of the reference runs applies to them.  The warp-specialised ring kernel
-(variant 10, an experiment that lost) only runs with GBP_TEST_EXPERIMENTAL=1."""
-import os
-
+"""GPU parity of the streaming build of the sweep kernel (kernel_variant 2: factored keyframe messages + early issue; what
+graphs of more than 8192 tiles get by default), forced onto the small fixture graphs so that every checkpoint of the
+reference runs applies to it, and of the shell cache (arena + CUDA graphs reused by the next graph of the same shape)."""
 import numpy as np
 import pytest
 
 from conftest import golden_configs, golden_problem, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
-EXPERIMENTAL = os.environ.get("GBP_TEST_EXPERIMENTAL", "0") not in ("", "0")
 
 
 @pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_float"])
 def test_factored_messages_against_reference_fixture(name):
-    """kernel_variant 7 (the build large graphs get by default) through every checkpoint of the reference run;
+    """kernel_variant 2 (the build large graphs get by default) through every checkpoint of the reference run;
     messages are read back in full form."""
     from gbp_b200.ba import create_ba_graph
     from test_ba_gpu import TOL_CONVERGED, TOL_EARLY, _check_snapshot, _run_loop
     G = load_golden(name)
-    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=7)
+    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=2)
     cks = set(G["checkpoints"].tolist())
     float_impl = bool(G["float_impl"])
 
@@ -39,7 +35,7 @@ def test_factored_messages_fr1desk_200_iterations():
     from gbp_b200.ba import create_ba_graph
     from test_ba_gpu import TOL_CONVERGED, _check_snapshot, _run_loop
     G = load_golden("fr1desk")
-    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=7)
+    graph = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=2)
     are, en, nrel = _run_loop(graph, G, 200)
     _check_snapshot(graph, G, "s199", TOL_CONVERGED)
     assert relerr(are, G["are"]) < 1e-6 and relerr(en, G["energy"]) < 1e-6
@@ -47,19 +43,16 @@ def test_factored_messages_fr1desk_200_iterations():
     graph.close()
 
 
-@pytest.mark.parametrize("variant", [5, 6, 7, 8, 9,
-                                     pytest.param(10, marks=pytest.mark.skipif(not EXPERIMENTAL, reason="ring kernel: set GBP_TEST_EXPERIMENTAL=1")),
-                                     pytest.param(12, marks=pytest.mark.skipif(not EXPERIMENTAL, reason="register column sums: not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1"))])
-def test_variants_equal_default_engine_and_round_trip(variant):
-    """Same graph, default engine vs variant, 64-edge tiles with landmark blocks (ragged tiles): same state; a message
-    table written by the client (full form) reads back unchanged and the sweep continues identically from it."""
+def test_streaming_build_equals_default_engine_and_round_trip():
+    """Same graph, full-row build vs streaming build, 64-edge tiles with landmark blocks (ragged tiles): same state; a
+    message table written by the client (full form) reads back unchanged and the sweep continues identically from it."""
     from gbp_b200 import _lib as L
     from gbp_b200.ba import create_ba_graph
     from gbp_b200.synthetic import make_synthetic
     prob = make_synthetic(20, 2000, 10, seed=0)
     cfg = dict(gauss_noise_std=2, loss="huber", Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
-    a = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512, kernel_variant=0)
-    b = create_ba_graph(prob, cfg, tile_edges=32 if variant == 10 else 64, lmk_block=512, kernel_variant=variant)
+    a = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512, kernel_variant=1)
+    b = create_ba_graph(prob, cfg, tile_edges=64, lmk_block=512, kernel_variant=2)
     for g in (a, b):
         g.generate_priors_var(50.0)
         g.update_all_beliefs()
@@ -79,62 +72,61 @@ def test_variants_equal_default_engine_and_round_trip(variant):
     a.close(); b.close()
 
 
-def test_programmatic_launches_do_not_change_results(monkeypatch):
-    """GBP_PDL=1: the kernels of captured iterations start early and synchronise on the device; bit-identical state."""
-    from gbp_b200 import _lib as L
-    from gbp_b200.ba import create_ba_graph
-    G = load_golden("fr1desk")
-    graphs = []
-    for pdl in ("0", "1"):
-        monkeypatch.setenv("GBP_PDL", pdl)
-        g = create_ba_graph(golden_problem(G), golden_configs(G))
-        g.generate_priors_var(50.0)
-        g.update_all_beliefs()
-        g.iterate(3, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
-        g.iterate(5, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
-        g.iterate(192, robustify=True, local_relin=True)
-        graphs.append(g)
-    a, b = graphs
-    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ITERS, L.F_FLAGS):
-        assert np.array_equal(a._eng.read(f), b._eng.read(f)), f
-    mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
-    assert relerr(b.get_means(), mu_ref) < 1e-4
-    a.close(); b.close()
-
-
 def test_layout_selection():
     """Small graphs keep the full message rows and the latency-oriented kernel; the factored layout is opt-in there."""
     from gbp_b200.ba import create_ba_graph
     G = load_golden("fr1desk_vsmall")
     a = create_ba_graph(golden_problem(G), golden_configs(G))
-    b = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=5)
-    assert (a._eng.msg_cam_width, a._eng.sweep_variant, a._eng.prefetch_tiles) == (27, 0, 0)
-    assert (b._eng.msg_cam_width, b._eng.sweep_variant) == (18, 5)
+    b = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=2)
+    assert (a._eng.msg_cam_width, a._eng.sweep_variant, a._eng.prefetch_tiles) == (27, 1, 0)
+    assert (b._eng.msg_cam_width, b._eng.sweep_variant, b._eng.prefetch_tiles) == (18, 2, 0)
     a.close(); b.close()
+    with pytest.raises(Exception):
+        create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=7)      # the round-1 experiments are gone
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="one-kernel iteration (variant 11): not yet run on hardware, set GBP_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("name", ["fr1desk", "fr1desk_vsmall_huber"])
-def test_one_kernel_iteration_equals_two_kernel_path(name):
-    """kernel_variant 11: sweep + belief update in one launch through completion counters; same fixed summation orders
-    as the two-kernel path, so the same bits; ba.py's schedule incl. the resets, 200 / 60 iterations."""
+def test_shell_cache_reuses_arena_and_graphs_without_changing_results():
+    """gbp_ba_destroy parks the arena + instantiated CUDA graphs; the next graph of the same shape picks them up (no
+    cudaMalloc / cudaGraphInstantiate) and produces bit-identical results; a graph of another shape reuses the arena only."""
     from gbp_b200 import _lib as L
     from gbp_b200.ba import create_ba_graph
-    G = load_golden(name)
-    n_iters = int(G["n_iters"])
-    graphs = []
-    for variant in (0, 11):
-        g = create_ba_graph(golden_problem(G), golden_configs(G), kernel_variant=variant)
+    G = load_golden("fr1desk_vsmall")
+    lib = L.load()
+    import ctypes as C
+
+    def stats():
+        out = (C.c_int64 * 6)()
+        L.check(lib.gbp_cache_stats(out))
+        return list(out)
+
+    def solve(cfg=None):
+        g = create_ba_graph(golden_problem(G), cfg or golden_configs(G))
         g.generate_priors_var(50.0)
         g.update_all_beliefs()
-        g.iterate(3, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
-        g.iterate(5, robustify=True, local_relin=True); g.reset_iters_since_relin(1)
-        g.iterate(n_iters - 8, robustify=True, local_relin=True)
-        graphs.append(g)
-    a, b = graphs
-    assert b._eng.launch_count() < a._eng.launch_count()             # really one launch per iteration
-    for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_LINPOINT, L.F_ITERS, L.F_FLAGS, L.F_ADAPTIVE_VAR):
-        assert np.array_equal(a._eng.read(f), b._eng.read(f)), f
-    key = f"s{int(G['checkpoints'].max())}"
-    assert relerr(b.get_means(), np.concatenate([G[f"{key}_cam_mu"].ravel(), G[f"{key}_lmk_mu"].ravel()])) < 1e-4
-    a.close(); b.close()
+        g.iterate(20, robustify=True, local_relin=True)
+        out = [g._eng.read(f).copy() for f in (L.F_CAM_BELIEF, L.F_LMK_BELIEF, L.F_MSG_CAM, L.F_MSG_LMK, L.F_ITERS)]
+        g.close()
+        return out
+
+    L.check(lib.gbp_cache_configure(0, 0))          # empty the cache: the first solve allocates
+    L.check(lib.gbp_cache_configure(4, 1 << 30))
+    s0 = stats()
+    first = solve()
+    s1 = stats()
+    assert s1[1] == s0[1] and s1[4] == 1            # nothing to reuse; one shell parked afterwards
+    second = solve()
+    s2 = stats()
+    assert s2[1] == s1[1] + 1 and s2[2] == s1[2] + 1   # arena AND graphs reused
+    for x, y in zip(first, second):
+        assert np.array_equal(x, y)
+    cfg = golden_configs(G)
+    cfg["beta"] = 0.02                               # other parameters: the captured launches are stale -> arena only
+    solve(cfg)
+    s3 = stats()
+    assert s3[1] == s2[1] + 1 and s3[2] == s2[2]
+    third = solve()                                  # the shape of `first` again, right after a different one: same bits
+    for x, y in zip(first, third):
+        assert np.array_equal(x, y)
+    L.check(lib.gbp_cache_configure(0, 0))
+    assert stats()[4] == 0
+    L.check(lib.gbp_cache_configure(4, 1 << 30))
