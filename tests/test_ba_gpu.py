@@ -459,7 +459,7 @@ def test_full_size_properties():
     g = create_ba_graph(prob, cfg)
     assert g._eng.F == 2_000_000 and g._eng.tile_edges == 64
     # large graphs get the bandwidth-oriented build: factored keyframe messages, early issue, L2 prefetch 38 k edges ahead
-    assert (g._eng.msg_cam_width, g._eng.sweep_variant, g._eng.prefetch_tiles) == (18, 7, 600)
+    assert (g._eng.msg_cam_width, g._eng.sweep_variant, g._eng.prefetch_tiles) == (18, 2, 600)
     g.generate_priors_var(50.0)
     g.update_all_beliefs()
     g.iterate(12, robustify=True, local_relin=True)
