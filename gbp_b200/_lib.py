@@ -22,6 +22,7 @@ ABI_VERSION = 1
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
+TUNE_RESIDENT, TUNE_RESIDENT_WARPS, TUNE_PREFETCH_TILES = 1, 2, 3
 
 # field -> (index kind, dtype, row width)
 FIELD_SHAPES = {
@@ -55,7 +56,7 @@ EXPORTS = [
     "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_p2p_init", "gbp_ba_p2p_attach", "gbp_ba_p2p_scatter", "gbp_ba_p2p_gather_update", "gbp_ba_p2p_status", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
     "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_plan_create", "gbp_plan_sizes", "gbp_plan_copy", "gbp_plan_destroy", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
-    "gbp_cache_configure", "gbp_cache_stats",
+    "gbp_cache_configure", "gbp_cache_stats", "gbp_ba_tune",
 ]
 
 _lib = None
@@ -127,6 +128,7 @@ def load():
     lib.gbp_bal_close.restype = None
     lib.gbp_cache_configure.argtypes = [C.c_int32, C.c_int64]
     lib.gbp_cache_stats.argtypes = [C.POINTER(C.c_int64)]
+    lib.gbp_ba_tune.argtypes = [vp, C.c_int, C.c_int64]
     if lib.gbp_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libgbp_b200 ABI {lib.gbp_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
