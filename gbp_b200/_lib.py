@@ -22,7 +22,7 @@ ABI_VERSION = 1
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
-TUNE_RESIDENT, TUNE_RESIDENT_WARPS, TUNE_PREFETCH_TILES = 1, 2, 3
+TUNE_PREFETCH_TILES = 3
 
 # field -> (index kind, dtype, row width)
 FIELD_SHAPES = {

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgbp_b200.so")
 SOURCES = ["gbp_ba.cu"]
-HEADERS = ["gbp_math.cuh", "gbp_edge.cuh", "gbp_kernels.cuh", "gbp_resident.cuh", "gbp_bal.cpp.inc", os.path.join("..", "..", "include", "gbp_b200.h")]
+HEADERS = ["gbp_math.cuh", "gbp_edge.cuh", "gbp_kernels.cuh", "gbp_bal.cpp.inc", os.path.join("..", "..", "include", "gbp_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,8 +44,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    extra = os.environ.get("GBP_NVCC_EXTRA", "").split()      # build-time only (e.g. -DGBP_RESIDENT_PROFILE for a profiling build)
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:

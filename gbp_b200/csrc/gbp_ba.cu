@@ -16,7 +16,6 @@
 
 #include "../../include/gbp_b200.h"
 #include "gbp_kernels.cuh"
-#include "gbp_resident.cuh"
 
 using namespace gbp;
 
@@ -108,18 +107,6 @@ struct gbp_ba_graph {
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
-
-    // resident kernel (gbp_resident.cuh): the whole gbp_ba_iterate(n) of an L2-resident graph in one cooperative launch
-    bool resident = false;           // tables built, shapes fit: gbp_ba_iterate uses it for n >= 2
-    bool resident_enabled = true;    // gbp_ba_tune(GBP_TUNE_RESIDENT, 0) switches back to the two-kernel iteration
-    bool resident_dirty = false;     // a resident launch since the error flag was last looked at
-    int res_warps = 1, n_sms = 148;
-    size_t res_smem = 0;             // dynamic shared memory per CTA
-    unsigned int res_epoch = 1;      // epoch of the next resident iteration (tags of the published rows; 0 = never written)
-    std::vector<ResidentTile> h_res_tiles;     // host copy: gbp_ba_tune(GBP_TUNE_RESIDENT_WARPS) deals the tiles to the CTAs again
-    DevBuf<int> res_b_chunks, res_cta_tiles, res_csr_pos;
-    DevBuf<ResidentTile> res_tile_info;
-    DevBuf<LLWord> res_pub_mq, res_pub_tq, res_pub_be, res_pub_cb;
 
     // peer-memory exchange (gbp_ba_p2p_*): own buffer, the peers' buffers as mapped here, device table of the bases
     char* xchg = nullptr;
@@ -260,8 +247,7 @@ ShapeKey make_key(const gbp_ba_graph* g) {
     ShapeKey k;
     memset(&k, 0, sizeof(k));
     k.device = g->device; k.C = g->C; k.L = g->L; k.T = g->T; k.n_tiles = g->n_tiles; k.cam_w = g->cam_w; k.pf_dist = g->pf_dist;
-    k.streaming = g->streaming ? 1 : 0; k.robust = g->robust ? 1 : 0;
-    k.resident = g->resident ? g->res_warps : 0;
+    k.streaming = g->streaming ? 1 : 0; k.robust = g->robust ? 1 : 0; k.resident = 0;
     k.F = g->F; k.n_slots = g->n_slots;
     k.cfg_d[0] = g->cfg.gauss_noise_std; k.cfg_d[1] = g->cfg.eta_damping; k.cfg_d[2] = g->cfg.beta; k.cfg_d[3] = g->cfg.Nstds;
     k.cfg_i[0] = g->cfg.num_undamped_iters; k.cfg_i[1] = g->cfg.min_linear_iters; k.cfg_i[2] = g->cfg.loss;
@@ -453,56 +439,6 @@ int iteration_stages(int robustify, int local_relin) {
     return st;
 }
 
-// n iterations of an L2-resident graph in one cooperative launch (gbp_resident.cuh) + one belief_kernel that refreshes the
-// belief arrays, means and keyframe partial sums from the final messages.
-template <bool ROBUST>
-int launch_resident_t(gbp_ba_graph* g, int stages, int n_iters) {
-    ResidentParams rp{};
-    rp.sweep = sweep_params(g, stages);
-    rp.pub_mq = g->res_pub_mq.p; rp.pub_tq = g->res_pub_tq.p; rp.pub_be = g->res_pub_be.p; rp.pub_cb = g->res_pub_cb.p;
-    rp.lmk_prior = g->lmk_prior.p; rp.cam_prior = g->cam_prior.p; rp.lmk_slots = g->lmk_slots.p; rp.csr_pos = g->res_csr_pos.p;
-    rp.cam_tile_ptr = g->cam_tile_ptr.p; rp.tile_info = g->res_tile_info.p; rp.b_chunks = g->res_b_chunks.p;
-    rp.cta_tiles = g->res_cta_tiles.p; rp.error_flag = g->metric_out.p + 3; rp.epoch0 = g->res_epoch;
-    rp.dbg = reinterpret_cast<long long*>(g->edge_max.p);
-    rp.n_iters = n_iters;
-    const int W = g->res_warps;
-    const int grid = (g->n_tiles + W - 1) / W;
-    const size_t smem = g->res_smem;
-    auto kernel = resident_kernel<ROBUST>;
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, W * 32, smem));
-    if ((long long)per_sm * g->n_sms < grid) return fail(GBP_ERR_STATE, "resident kernel: %d CTAs do not fit the device at once", grid);
-    void* args[] = {(void*)&rp};
-    CU(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3((unsigned)(W * 32)), args, smem, g->stream));
-    g->launches++;
-    g->resident_dirty = true;
-    g->res_epoch += (unsigned int)n_iters;
-    return GBP_OK;
-}
-
-int launch_resident(gbp_ba_graph* g, int stages, int n_iters) {
-    int rc = g->robust ? launch_resident_t<true>(g, stages, n_iters) : launch_resident_t<false>(g, stages, n_iters);
-    if (rc != GBP_OK) return rc;
-    return launch_belief(g, 1);
-}
-
-// The resident kernel raises metric_out[3] when one of its waits timed out (the state is then invalid).  Looked at wherever the
-// stream is synchronised anyway.
-int check_error_flag(gbp_ba_graph* g) {
-    if (!g->resident_dirty) return GBP_OK;
-    double flag = 0.0;
-    CU(cudaMemcpyAsync(&flag, g->metric_out.p + 3, sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-    CU(cudaStreamSynchronize(g->stream));
-    g->resident_dirty = false;
-    g->res_epoch = 1;      // the published rows were zeroed with the zero region
-    if (flag != 0.0) {
-        g->resident = false;      // fall back to the two-kernel iteration until the graph is reset
-        return fail(GBP_ERR_STATE, "resident kernel: a grid-wide wait timed out; the graph state is invalid (gbp_ba_reset to start over)");
-    }
-    return GBP_OK;
-}
-
 
 // ----------------------------------------------------------------------------------------
 // Host graph compiler: measurement list -> engine storage order.  Pure host code (no CUDA call), so it is also
@@ -627,81 +563,6 @@ int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* 
     return GBP_OK;
 }
 
-// Resident kernel, phase B: which warp owns which landmarks / keyframe.  Keyframe c goes to warp c * tiles / C (at most one per
-// warp); the landmarks are dealt in index order to the other warps in contiguous runs of about F / warps message rows (a warp's
-// rows are then one contiguous range of the landmark CSR), at most 32 chunks of <= 8 rows per warp (one lane per chunk; the chunks
-// of a landmark sit on consecutive lanes, the first one leads).  Fills h_res_tiles (all but smem_off) and the per-lane roles.
-int plan_resident(gbp_ba_graph* g, const GraphPlan& plan, std::vector<int>* b_chunks) {
-    const int nt = g->n_tiles, C = g->C, L = g->L;
-    g->h_res_tiles.assign((size_t)nt, ResidentTile{0, 0, 0, -1, 0, 0});
-    for (int c = 0; c < C; ++c) {
-        if (plan.cam_tile_ptr[c + 1] - plan.cam_tile_ptr[c] > RES_MAX_CAM_TILES) return fail(GBP_ERR_STATE, "resident kernel: keyframe %d has too many tiles", c);
-        g->h_res_tiles[(size_t)((long long)c * nt / C)].b_cam = c;
-    }
-    int free_warps = 0;
-    for (int t = 0; t < nt; ++t) free_warps += g->h_res_tiles[t].b_cam < 0;
-    const bool owners_too = free_warps * 24 < nt;                 // hardly any warp without a keyframe: everybody takes landmarks
-    const long long F = g->F;
-    std::vector<int> takers;                      // the warps that take landmarks, in order
-    for (int t = 0; t < nt; ++t)
-        if (owners_too || g->h_res_tiles[t].b_cam < 0) takers.push_back(t);
-    const long long nw = (long long)takers.size();
-    // landmark l goes to taker floor(rows before l * takers / F): contiguous runs of F / takers rows, give or take one landmark
-    b_chunks->assign((size_t)nt * 64, 0);
-    long long before = 0;
-    for (int l = 0; l < L; ++l) {
-        const int p0 = plan.lmk_ptr[l], deg = plan.lmk_ptr[l + 1] - p0;
-        if (deg == 0) continue;
-        const int nch = (deg + RES_CHUNK - 1) / RES_CHUNK;
-        const int w = takers[(size_t)std::min(nw - 1, before * nw / std::max<long long>(F, 1))];
-        ResidentTile& ti = g->h_res_tiles[w];
-        if (nch > 32 || ti.b_nchunks + nch > 32 || ti.b_rows + deg > RES_MAX_B_ROWS)
-            return fail(GBP_ERR_STATE, "resident kernel: landmark %d (%d edges) does not fit its warp", l, deg);
-        if (ti.b_rows == 0) ti.b_q0 = p0;
-        for (int c = 0; c < nch; ++c) {
-            const int cnt = std::min(RES_CHUNK, deg - c * RES_CHUNK);
-            (*b_chunks)[((size_t)w * 32 + ti.b_nchunks + c) * 2] = ((ti.b_rows + c * RES_CHUNK) << 16) | (cnt << 12) | (c << 6) | nch;
-            (*b_chunks)[((size_t)w * 32 + ti.b_nchunks + c) * 2 + 1] = l;
-        }
-        ti.b_rows += deg; ti.b_nchunks += nch;
-        before += deg;
-    }
-    return GBP_OK;
-}
-
-// Resident kernel: which tile goes to which warp of which CTA.  A warp's shared-memory block depends on what it owns in phase B,
-// so the tiles are dealt largest first to the CTA with the smallest total so far (W tiles per CTA).  Fills smem_off of the host
-// tile table, *cta_tiles ([grid][W], -1 = none) and g->res_smem.
-int deal_resident_tiles(gbp_ba_graph* g, const std::vector<Tile>& tiles, const std::vector<int>& cam_tile_ptr, std::vector<int>* cta_tiles) {
-    (void)tiles;
-    const int nt = g->n_tiles, W = g->res_warps;
-    const int grid = (nt + W - 1) / W;
-    if ((long long)grid * W > (long long)g->n_sms * RES_MAX_WARPS) return fail(GBP_ERR_STATE, "resident kernel: %d CTAs of %d tiles exceed the %d SMs", grid, W, g->n_sms);
-    std::vector<size_t> need((size_t)nt);
-    std::vector<int> order((size_t)nt);
-    for (int t = 0; t < nt; ++t) {
-        const int c = g->h_res_tiles[t].b_cam;
-        need[t] = (resident_tile_smem(g->h_res_tiles[t].b_rows, c >= 0 ? cam_tile_ptr[c + 1] - cam_tile_ptr[c] : 0) + 15) & ~size_t(15);
-        order[t] = t;
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return need[a] > need[b]; });
-    std::vector<size_t> total((size_t)grid, 0);
-    std::vector<int> count((size_t)grid, 0);
-    cta_tiles->assign((size_t)g->n_sms * RES_MAX_WARPS * RES_MAX_WARPS, -1);
-    for (int t : order) {
-        int best = -1;
-        for (int b = 0; b < grid; ++b)
-            if (count[b] < W && (best < 0 || total[b] < total[best])) best = b;
-        g->h_res_tiles[t].smem_off = (int)total[best];
-        (*cta_tiles)[(size_t)best * W + count[best]] = t;
-        total[best] += need[t];
-        count[best]++;
-    }
-    g->res_smem = *std::max_element(total.begin(), total.end());
-    if (g->res_smem > 220 * 1024) return fail(GBP_ERR_STATE, "resident kernel: %zu bytes of shared memory per CTA", g->res_smem);
-    return GBP_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -778,23 +639,6 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         g->pf_dist = g->n_tiles > 8192 ? (int)std::min<long long>(38400 / T, std::max(1, g->n_tiles / 32)) : 0;
     }
 
-    // ---------------- resident kernel: static per-tile tables (small graphs only) ----------------
-    // A tile's warp recomputes the beliefs it reads from what the other tiles publish; it needs (i) for every edge the chunks of
-    // its landmark's message list (<= 8 rows each, CSR order: the summation order of belief_kernel<32>) and (ii) the tiles of its
-    // keyframe in cam_tiles order.  Built when every tile can own a warp for the whole call.
-    std::vector<int> h_b_chunks, h_cta_tiles, h_csr_pos;
-    cudaDeviceGetAttribute(&g->n_sms, cudaDevAttrMultiProcessorCount, device);
-    if (cfg->kernel_variant == 0 && !g->streaming && T == 32 && g->n_tiles > 0 && g->n_tiles <= g->n_sms * RES_MAX_WARPS && C <= g->n_tiles) {
-        g->res_warps = std::min(RES_MAX_WARPS, (g->n_tiles + g->n_sms - 1) / g->n_sms);
-        g->resident = plan_resident(g, plan, &h_b_chunks) == GBP_OK && deal_resident_tiles(g, tiles, plan.cam_tile_ptr, &h_cta_tiles) == GBP_OK;
-        if (!g->resident) g->h_res_tiles.clear();
-        if (g->resident) {
-            h_csr_pos.assign((size_t)g->n_slots, 0);
-            for (size_t q = 0; q < plan.lmk_slots.size(); ++q) h_csr_pos[(size_t)plan.lmk_slots[q]] = (int)q;
-            for (size_t q = 0; q < plan.cam_tiles.size(); ++q) g->h_res_tiles[(size_t)plan.cam_tiles[q]].cam_pos = (int)q;
-        }
-    }
-
     // ---------------- device allocation + upload ----------------
     auto bail = [&](cudaError_t e, const char* what) { return fail(GBP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
     cudaError_t e;
@@ -815,19 +659,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(z, S * 2); ALLOC(slot_of_factor, (size_t)F);
         ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F); ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
         ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
-        if (g->resident) {
-            ALLOC(res_b_chunks, h_b_chunks.size()); ALLOC(res_tile_info, g->h_res_tiles.size()); ALLOC(res_csr_pos, S);
-            ALLOC(res_cta_tiles, (size_t)g->n_sms * RES_MAX_WARPS * RES_MAX_WARPS);
-        }
         g->upload_bytes = A.used - g->upload_off;
         // zero region: everything gbp_ba_reset clears, contiguous -> ONE memset
         zero_off = A.used;
         ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M);
         ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
         ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
-        if (g->resident) {      // tagged rows: epoch 0 = never written
-            ALLOC(res_pub_mq, (size_t)F * LMK_M); ALLOC(res_pub_tq, tiles.size() * CAM_M); ALLOC(res_pub_be, S * LMK_B); ALLOC(res_pub_cb, (size_t)C * CAM_B);
-        }
         zero_end = A.used;
         ALLOC(iters, S); ALLOC(flags, S); ALLOC(linpoint, S * 9); ALLOC(sigma2a, S);
         ALLOC(tile_metric, tiles.size() * 3);
@@ -851,18 +688,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     g->zero_bytes = zero_end - zero_off;
     {
         struct Up { const void* src; size_t bytes; void* dst; };
-        std::vector<Up> ups = {
+        const Up ups[] = {
             {tiles.data(), tiles.size() * sizeof(Tile), g->tiles.p}, {plan.lmk_idx.data(), plan.lmk_idx.size() * 4, g->lmk_idx.p},
             {plan.z.data(), plan.z.size() * 8, g->z.p}, {g->h_slot_of_factor.data(), g->h_slot_of_factor.size() * 4, g->slot_of_factor.p},
             {plan.lmk_ptr.data(), plan.lmk_ptr.size() * 4, g->lmk_ptr.p}, {plan.lmk_slots.data(), plan.lmk_slots.size() * 4, g->lmk_slots.p},
             {plan.cam_tile_ptr.data(), plan.cam_tile_ptr.size() * 4, g->cam_tile_ptr.p}, {plan.cam_tiles.data(), plan.cam_tiles.size() * 4, g->cam_tiles.p},
             {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p}};
-        if (g->resident) {
-            ups.push_back({h_b_chunks.data(), h_b_chunks.size() * 4, g->res_b_chunks.p});
-            ups.push_back({h_csr_pos.data(), h_csr_pos.size() * 4, g->res_csr_pos.p});
-            ups.push_back({g->h_res_tiles.data(), g->h_res_tiles.size() * sizeof(ResidentTile), g->res_tile_info.p});
-            ups.push_back({h_cta_tiles.data(), h_cta_tiles.size() * 4, g->res_cta_tiles.p});
-        }
         constexpr size_t STAGE_MAX = size_t(32) << 20;   // larger graphs upload table by table (a page-locked block that size costs more than it saves)
         if (g->upload_bytes <= STAGE_MAX) {
             if (g->stage_bytes < g->upload_bytes) {
@@ -942,10 +773,7 @@ int gbp_cache_stats(int64_t out[6]) {
 int gbp_ba_reset(gbp_handle h) {
     CHECK_H(h);
     gbp_ba_graph* g = h;
-    if (g->zero_bytes) CU(cudaMemsetAsync(g->arena.base + g->zero_off, 0, g->zero_bytes, g->stream));   // messages, priors, partial sums, prior scans, barrier words
-    CU(cudaMemsetAsync(g->metric_out.p, 0, 4 * sizeof(double), g->stream));                              // metrics + the error flag (metric_out[3])
-    g->resident_dirty = false;
-    g->res_epoch = 1;      // the published rows were zeroed with the zero region
+    if (g->zero_bytes) CU(cudaMemsetAsync(g->arena.base + g->zero_off, 0, g->zero_bytes, g->stream));   // messages, priors, partial sums, prior scans
     // beliefs: eta = Lambda = 0, mu = initial means; edges linearised at those means
     if (g->C > 0) init_belief_kernel<<<(g->C + 127) / 128, 128, 0, g->stream>>>(g->cam_mu0.p, g->C, 6, CAM_B, g->cam_belief.p, g->cam_mu.p);
     if (g->L > 0) init_belief_kernel<<<(g->L + 127) / 128, 128, 0, g->stream>>>(g->lmk_mu0.p, g->L, 3, LMK_B, g->lmk_belief.p, g->lmk_mu.p);
@@ -977,7 +805,7 @@ int gbp_ba_layout(gbp_handle h, int64_t out[4]) {
     out[0] = h->cam_w;                 // doubles per stored factor->keyframe message: 27 (full) or 18 (factored)
     out[1] = h->pf_dist;               // L2 prefetch distance in tiles (0 = off)
     out[2] = h->streaming ? 2 : 1;     // sweep kernel build in use (gbp_config.kernel_variant after the automatic choice)
-    out[3] = h->resident ? h->res_warps : 0;   // resident kernel available (tiles per CTA), 0 = two-kernel iteration only
+    out[3] = 0;                        // reserved
     return GBP_OK;
 }
 
@@ -1161,7 +989,6 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (n_iters < 0) return fail(GBP_ERR_INVALID, "n_iters < 0");
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
-    if (h->resident && h->resident_enabled && n_iters >= 2) return launch_resident(h, st, n_iters);
     constexpr int REPS = 8;
     const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
     int left = n_iters;
@@ -1200,7 +1027,7 @@ int gbp_ba_metrics(gbp_handle h, double out[3]) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, h->metric_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return check_error_flag(h);
+    return GBP_OK;
 }
 
 namespace {
@@ -1310,10 +1137,6 @@ int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes) {
     if (need == 0) return GBP_OK;
     if (!host_dst) return fail(GBP_ERR_INVALID, "null destination");
     if (field == GBP_F_ADJ) { memcpy(host_dst, h->h_adj.data(), need); return GBP_OK; }
-    {
-        int rc = check_error_flag(h);
-        if (rc != GBP_OK) return rc;
-    }
     if (field == GBP_F_FILE_INDEX) { memcpy(host_dst, h->h_file_of_factor.data(), need); return GBP_OK; }
     if (fi.indexed != 2) {
         CU(cudaMemcpyAsync(host_dst, field_dev_ptr(h, field), need, cudaMemcpyDeviceToHost, h->stream));
@@ -1414,34 +1237,12 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
 int gbp_ba_synchronize(gbp_handle h) {
     CHECK_H(h);
     CU(cudaStreamSynchronize(h->stream));
-    return check_error_flag(h);
+    return GBP_OK;
 }
 
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value) {
     CHECK_H(h);
     switch (knob) {
-        case GBP_TUNE_RESIDENT:
-            h->resident_enabled = value != 0;
-            return GBP_OK;
-        case GBP_TUNE_RESIDENT_WARPS: {
-            if (!h->resident) return fail(GBP_ERR_STATE, "this graph has no resident kernel");
-            if (value < 1 || value > RES_MAX_WARPS) return fail(GBP_ERR_INVALID, "tiles per CTA must be 1..%d", RES_MAX_WARPS);
-            CU(cudaStreamSynchronize(h->stream));
-            const int old_w = h->res_warps;
-            std::vector<Tile> tiles((size_t)h->n_tiles);
-            std::vector<int> ctp((size_t)h->C + 1), cta;
-            CU(cudaMemcpy(tiles.data(), h->tiles.p, tiles.size() * sizeof(Tile), cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(ctp.data(), h->cam_tile_ptr.p, ctp.size() * 4, cudaMemcpyDeviceToHost));
-            h->res_warps = (int)value;
-            int rc = deal_resident_tiles(h, tiles, ctp, &cta);
-            if (rc != GBP_OK) {
-                h->res_warps = old_w;
-                deal_resident_tiles(h, tiles, ctp, &cta);
-            }
-            CU(cudaMemcpy(h->res_tile_info.p, h->h_res_tiles.data(), h->h_res_tiles.size() * sizeof(ResidentTile), cudaMemcpyHostToDevice));
-            CU(cudaMemcpy(h->res_cta_tiles.p, cta.data(), cta.size() * 4, cudaMemcpyHostToDevice));
-            return rc;
-        }
         case GBP_TUNE_PREFETCH_TILES:
             if (value < 0) return fail(GBP_ERR_INVALID, "prefetch distance must be >= 0");
             CU(cudaStreamSynchronize(h->stream));
@@ -1518,15 +1319,6 @@ int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_r
 }
 
 int64_t gbp_ba_launch_count(gbp_handle h) { return h ? h->launches : 0; }
-
-#ifdef GBP_RESIDENT_PROFILE
-int gbp_debug_read_edge_max(gbp_handle h, void* dst, size_t bytes) {      // profiling builds only: the stamp buffer of the resident kernel
-    CHECK_H(h);
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(dst, h->edge_max.p, std::min(bytes, h->edge_max.bytes()), cudaMemcpyDeviceToHost));
-    return GBP_OK;
-}
-#endif
 
 int gbp_reprojection_eval(const double* x, int64_t n, const double K[4], int device, double* out_h, double* out_J) {
     if (!x || !K || !out_h || !out_J || n < 0) return fail(GBP_ERR_INVALID, "bad argument");

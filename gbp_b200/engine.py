@@ -64,7 +64,6 @@ class BAEngine:
         L.check(lib.gbp_ba_layout(h, lay))
         # doubles per stored factor->keyframe message (27 full / 18 factored), L2 prefetch distance, sweep kernel build
         self.msg_cam_width, self.prefetch_tiles, self.sweep_variant = int(lay[0]), int(lay[1]), int(lay[2])
-        self.resident_warps = int(lay[3])      # tiles per CTA of the resident kernel; 0 = two-kernel iteration only
         self.K4 = K4
         self.device = int(device)
 
@@ -84,10 +83,8 @@ class BAEngine:
         L.check(self._lib.gbp_ba_reset(self._h))
 
     def tune(self, knob, value):
-        """Engine tuning knobs (L.TUNE_*): resident kernel on / off, its tiles per CTA, L2 prefetch distance."""
+        """Engine tuning knobs (L.TUNE_*; measurement scripts): the L2 prefetch distance of the streaming build."""
         L.check(self._lib.gbp_ba_tune(self._h, int(knob), int(value)))
-        if knob == L.TUNE_RESIDENT_WARPS:
-            self.resident_warps = int(value)
         if knob == L.TUNE_PREFETCH_TILES:
             self.prefetch_tiles = int(value) if self.sweep_variant == 2 else 0
 

@@ -57,8 +57,7 @@ typedef struct gbp_config {
     int32_t lmk_block;           /* 0 = auto; landmarks per L2 block of the edge schedule      */
     int32_t kernel_variant;      /* build of the sweep kernel: 0 = automatic (graphs of up to 8192 tiles live in L2 and get build 1,
                                     larger ones stream from HBM and get build 2);
-                                    1 = full 27-double factor->keyframe message rows, bulk copies sized by the tile descriptor, always the
-                                        two-kernel iteration (no resident kernel);
+                                    1 = full 27-double factor->keyframe message rows, bulk copies sized by the tile descriptor;
                                     2 = streaming build: factor->keyframe messages stored with their rank-2 precision factored
                                         (eta[6] | W[2][6], Lambda = W^T W: 144 B less traffic per edge and sweep), nothing in the
                                         prologue waits for the tile descriptor, far-ahead L2 prefetch on graphs of more than 8192
@@ -146,8 +145,7 @@ void gbp_plan_destroy(gbp_plan p);
 
 /* Engine layout chosen for this graph (no reference counterpart; used by bench.py to count the bytes a sweep moves):
  * out[0] doubles per stored factor->keyframe message (27 full, 18 factored), out[1] L2 prefetch distance in tiles,
- * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice: 1 or 2), out[3] tiles per CTA of the
- * resident kernel (0 = this graph only has the two-kernel iteration). */
+ * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice: 1 or 2), out[3] reserved (0). */
 int gbp_ba_layout(gbp_handle h, int64_t out[4]);
 
 /* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
@@ -193,10 +191,8 @@ int gbp_ba_p2p_scatter(gbp_handle h);
 int gbp_ba_p2p_gather_update(gbp_handle h);
 int gbp_ba_p2p_status(gbp_handle h, int64_t out[2]);
 /* n x synchronous_iteration(robustify, local_relin) on one GPU (gbp/gbp.py:86-92; the loop of
- * ba.py:84-105 without the client's per-iteration reads).  Graphs that live in L2 (kernel_variant 0, 32-edge tiles, at most
- * 8 tiles per SM) run the whole call as ONE cooperative launch of the resident kernel (gbp_resident.cuh; one grid barrier per
- * iteration, bit-identical state) when n >= 2; otherwise [sweep_kernel, belief_kernel] per iteration, replayed from a CUDA
- * graph.  Enqueued on the handle's stream, no host synchronisation. */
+ * ba.py:84-105 without the client's per-iteration reads): sweep_local + cam_update, replayed from a
+ * CUDA graph. */
 int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin);
 /* FactorGraph.update_all_beliefs alone (gbp/gbp.py:56-58), single GPU. */
 int gbp_ba_update_beliefs(gbp_handle h);
@@ -236,10 +232,9 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
                       int32_t min_linear_iters);
 
 int gbp_ba_synchronize(gbp_handle h);
-/* Engine tuning knobs (no reference counterpart; measurement scripts and tests): GBP_TUNE_RESIDENT 0 / 1 = gbp_ba_iterate
- * uses the two-kernel iteration / the resident kernel (default 1 where the graph has one); GBP_TUNE_RESIDENT_WARPS = tiles
- * per CTA of the resident kernel (1..8); GBP_TUNE_PREFETCH_TILES = L2 prefetch distance of the streaming build in tiles. */
-enum { GBP_TUNE_RESIDENT = 1, GBP_TUNE_RESIDENT_WARPS = 2, GBP_TUNE_PREFETCH_TILES = 3 };
+/* Engine tuning knobs (no reference counterpart; measurement scripts): GBP_TUNE_PREFETCH_TILES = L2 prefetch distance of the
+ * streaming build in tiles (0 = off; the automatic choice is ~38 k edges ahead). */
+enum { GBP_TUNE_PREFETCH_TILES = 3 };
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value);
 /* Timing helper for benchmarks: runs n_iters iterations bracketed by CUDA events on the handle's
  * stream; *ms_total = elapsed device time, *ms_msg_kernel = summed time of the message kernel alone

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B timings of the engine's tuning knobs on one GPU (a few seconds each):
 
-  fr1desk   200-iteration solve (the bench's `value` workload): two-kernel iteration vs resident kernel at 1..8 tiles per CTA
+  fr1desk   200-iteration solve (the bench's `value` workload), repeated runs
   synthetic 1k / 1M / 10M graph, per-kernel CUDA-event timing of the sweep: tile size, landmark block, L2 prefetch distance
 
 Every run's final means are compared with the first run's (and fr1desk with the reference fixture).
@@ -48,15 +48,11 @@ def fr1desk(reps):
     prob = balio.BALProblem(G["in_cam_id"], G["in_lmk_id"], G["in_z"], G["in_cam0"], G["in_lmk0"], G["in_K"])
     mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
     base = None
-    runs = [("two_kernel", 0)] + [(f"resident_w{w}", w) for w in (0, 1, 2, 3, 4, 8)] + [("two_kernel_again", 0)]
+    runs = [("run1", 0), ("run2", 0)]
     for tag, w in runs:
         try:
             g = create_ba_graph(prob, CFG)
             e = g._eng
-            if tag.startswith("two_kernel"):
-                e.tune(L.TUNE_RESIDENT, 0)
-            elif w:
-                e.tune(L.TUNE_RESIDENT_WARPS, w)
             times = []
             for it in range(reps + 2):
                 g.reset()
@@ -71,8 +67,7 @@ def fr1desk(reps):
             mu = g.get_means()
             if base is None:
                 base = mu
-            emit({"graph": "fr1desk", "run": tag, "tiles_per_cta": e.resident_warps if not tag.startswith("two_kernel") else None,
-                  "ms_per_solve_wall_min": 1e3 * min(times), "ms_per_solve_wall_median": 1e3 * float(np.median(times)),
+            emit({"graph": "fr1desk", "run": tag, "ms_per_solve_wall_min": 1e3 * min(times), "ms_per_solve_wall_median": 1e3 * float(np.median(times)),
                   "us_per_iteration_min": 1e6 * min(times) / 200, "rel_err_vs_reference": float(np.max(np.abs(mu - mu_ref)) / np.max(np.abs(mu_ref))),
                   "max_abs_diff_vs_first": float(np.max(np.abs(mu - base))), "are": g.are()})
             g.close()
