@@ -508,6 +508,48 @@ def bench_synthetic_1gpu(ctx, args):
     return synth, roof
 
 
+def phase_breakdown(ctx, pg, n=30):
+    """Where an iteration of the partitioned graph spends its time on this rank: the same calls as
+    PartitionedBAGraph.synchronous_iteration, issued eagerly with CUDA events between the phases (medians over n iterations,
+    max over ranks).  Eager launches have gaps the captured graph does not, so the sum is an upper bound of the captured iteration."""
+    from gbp_b200 import _lib as L
+    torch = ctx.torch
+    a = pg.adapter
+    st = L.ST_MESSAGES | L.ST_BELIEFS | L.ST_DEFER_LANDMARKS | L.ST_ROBUSTIFY | L.ST_RELIN | L.ST_LOCAL_DAMPING
+    rows = []
+    for it in range(n + 5):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        with pg._stream_ctx():
+            ev[0].record()
+            a.sweep_local(st)                       # sweep_kernel + keyframe partial sums (belief_kernel, keyframe part)
+            ev[1].record()
+            if pg.p2p:
+                a.p2p_scatter()
+                ev[2].record()
+                a.landmark_update()
+                ev[3].record()
+                a.p2p_gather_update()
+            else:
+                work = pg.dist.all_gather_into_tensor(pg._gather, a.partial_tensor(), async_op=True)
+                ev[2].record()
+                a.landmark_update()
+                ev[3].record()
+                work.wait()
+                a.apply_gathered(pg._gather, pg.world)
+            ev[4].record()
+        torch.cuda.synchronize()
+        pg.n_iterations += 1
+        if it >= 5:
+            rows.append([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(4)] + [ev[0].elapsed_time(ev[4]) * 1e3])
+    med = np.median(np.array(rows), axis=0)
+    med = [ctx.max_over_ranks(float(x)) for x in med]
+    names = ["local_sweep_and_keyframe_partial_sums", "exchange_issue" if not pg.p2p else "peer_memory_scatter", "landmark_belief_update",
+             "exchange_wait_and_keyframe_update", "total_eager"]
+    out = dict(zip(names, med))
+    out["note"] = "eager launches with CUDA events between the phases, median of %d iterations, max over ranks; the timed solve replays a captured graph without the launch gaps" % n
+    return out
+
+
 def bench_partitioned(ctx, args):
     """N > 1: configs[4], the synthetic graph landmark-partitioned over the ranks; headline of the line (strong scaling)."""
     torch, dist, rank, world = ctx.torch, ctx.dist, ctx.rank, ctx.world
@@ -561,6 +603,7 @@ def bench_partitioned(ctx, args):
     t_dev = ctx.max_over_ranks(float(np.sum(step_ms)) / 1e3)
     ctx.barrier()
     n_applied = pg.n_iterations
+    breakdown = phase_breakdown(ctx, pg)
     are, energy, nrel = pg.metrics()
     means = pg.get_means()                     # collective: every rank
     status = pg.adapter.p2p_status() if pg.p2p else None
@@ -643,6 +686,7 @@ def bench_partitioned(ctx, args):
                     "what": "per rank, from the host arrays of the whole problem: cut out the local landmark block, compile + upload the local graph, priors (cross-rank max), capture, 200 synchronous iterations, local means back on the host; wall clock, max over ranks"},
             "gpu_launches": per_iter_launches * S * args.steps,
             "gpu_launches_note": f"{per_iter_launches} kernels of this library per iteration and rank (sweep, keyframe partial sums, landmark beliefs, keyframe update) + the exchange; counted on rank 0",
+            "iteration_phases_us": breakdown,
             "parity_vs_1gpu": par, "are_px_after": are, "energy_after": energy,
             "generate_s": gen_s, "graph_build_s": build_s, "fr1desk_replicas": fr1, "peak_source": ctx.peak_src,
             "roofline": None, "cpu_baseline": None,

@@ -57,6 +57,8 @@ EXPORTS = [
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
     "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_plan_create", "gbp_plan_sizes", "gbp_plan_copy", "gbp_plan_destroy", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
     "gbp_cache_configure", "gbp_cache_stats", "gbp_ba_tune",
+    "gbp_lin_create", "gbp_lin_destroy", "gbp_lin_set_messages", "gbp_lin_update_beliefs", "gbp_lin_iterate", "gbp_lin_energy", "gbp_lin_read",
+    "gbp_lin_joint_solve", "gbp_lin_launch_count",
 ]
 
 _lib = None
@@ -129,6 +131,16 @@ def load():
     lib.gbp_cache_configure.argtypes = [C.c_int32, C.c_int64]
     lib.gbp_cache_stats.argtypes = [C.POINTER(C.c_int64)]
     lib.gbp_ba_tune.argtypes = [vp, C.c_int, C.c_int64]
+    lib.gbp_lin_create.argtypes = [C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int, vp, C.POINTER(vp)]
+    lib.gbp_lin_destroy.argtypes = [vp]
+    lib.gbp_lin_set_messages.argtypes = [vp, vp, vp]
+    lib.gbp_lin_update_beliefs.argtypes = [vp]
+    lib.gbp_lin_iterate.argtypes = [vp, C.c_int]
+    lib.gbp_lin_energy.argtypes = [vp, dp]
+    lib.gbp_lin_read.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.gbp_lin_joint_solve.argtypes = [vp, vp, vp, vp, vp]
+    lib.gbp_lin_launch_count.argtypes = [vp]
+    lib.gbp_lin_launch_count.restype = C.c_int64
     if lib.gbp_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libgbp_b200 ABI {lib.gbp_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib

@@ -1392,3 +1392,4 @@ void gbp_plan_destroy(gbp_plan p) { delete p; }
 }  // extern "C"
 
 #include "gbp_bal.cpp.inc"
+#include "gbp_lin.cu.inc"

@@ -1,9 +1,12 @@
-"""Generic factor graph with arbitrary Python measurement callables (host, NumPy).
+"""Generic factor graph with arbitrary Python measurement callables.
 
 Mirror of the reference's ``gbp/gbp.py`` classes ``FactorGraph`` / ``VariableNode`` / ``Factor``
-for the one configuration that is host plumbing by contract (BASELINE config 1:
-``ndim_posegraph.py``, linear displacement factors built from Python callables).  The
-bundle-adjustment path never uses this module: reprojection graphs are built by
+for graphs the client assembles object by object (BASELINE config 1: ``ndim_posegraph.py``,
+linear displacement factors built from Python callables).  The arithmetic here is host NumPy --
+config 1 is CPU plumbing by contract -- but a graph of pairwise LINEAR factors between variables
+of equal dimension <= 6 moves onto the GPU engine of ``gbp_b200.lingraph``
+when a CUDA device is present: ``USE_DEVICE`` = None (automatic) / True (required) / False (host).
+The bundle-adjustment path never uses this module: reprojection graphs are built by
 ``gbp_b200.ba`` and run on the GPU.
 
 Same constructor signatures, attribute names and update rules as the reference:
@@ -17,6 +20,13 @@ from __future__ import annotations
 import numpy as np
 
 from .gaussian import NdimGaussian
+
+import os as _os
+
+# None: device when available and the graph qualifies; True: must; False: never.  An UNMODIFIED client script cannot set this, so
+# the launcher honours GBP_LINEAR_DEVICE=0 / 1 (python -m gbp_b200.run ndim_posegraph.py).
+USE_DEVICE = {"0": False, "1": True}.get(_os.environ.get("GBP_LINEAR_DEVICE", ""), None)
+SYNC_OBJECTS_MAX = 4096    # graphs up to this many variables / factors refresh the node / factor objects after every device call
 
 
 def _mean_of(g):
@@ -152,11 +162,65 @@ class FactorGraph:
             self.beta = beta
             self.num_undamped_iters = num_undamped_iters
             self.min_linear_iters = min_linear_iters
+        self._dev = None            # gbp_b200.lingraph.LinearGraphEngine once the graph runs on the GPU
+        self._dev_tried = False
+
+    # ------------------------------------------------------------------ device backend (linear pairwise graphs)
+    def device_backend(self):
+        """The GPU engine of this graph, built from the objects on first use (after compute_all_factors: the factors'
+        linearisation points must exist), or None when the graph stays on the host."""
+        if self._dev is not None or self._dev_tried or USE_DEVICE is False:
+            return self._dev
+        self._dev_tried = True
+        from . import lingraph
+        if not lingraph.device_available():
+            if USE_DEVICE:
+                raise RuntimeError("hostgraph.USE_DEVICE is True but no CUDA device / library is available")
+            return None
+        t = lingraph.tables_from_host_graph(self)
+        if t is None:
+            if USE_DEVICE:
+                raise RuntimeError("hostgraph.USE_DEVICE is True but this graph is not a pairwise linear graph of equal dofs <= 6")
+            return None
+        msg_eta, msg_lam = t.pop("msg_eta"), t.pop("msg_lam")
+        self._dev = lingraph.LinearGraphEngine(eta_damping=self.eta_damping, **t)
+        if np.any(msg_eta) or np.any(msg_lam):
+            self._dev.set_messages(msg_eta, msg_lam)
+        self._dev.update_beliefs()
+        return self._dev
+
+    def _objects_from_device(self, force=False):
+        """Beliefs, means and messages of the device graph back into the VariableNode / Factor objects."""
+        d = self._dev
+        if d is None or (not force and max(len(self.var_nodes), len(self.factors)) > SYNC_OBJECTS_MAX):
+            return
+        eta, lam, mu = d.beliefs()
+        for k, v in enumerate(self.var_nodes):
+            v.belief.eta, v.belief.lam, v.mu = eta[k].copy(), lam[k].copy(), mu[k].copy()
+            v.Sigma = np.linalg.inv(lam[k])
+        meta, mlam = d.messages()
+        index = {id(v): k for k, v in enumerate(self.var_nodes)}
+        for k, f in enumerate(self.factors):
+            for side in (0, 1):
+                f.messages[side].eta, f.messages[side].lam = meta[2 * k + side].copy(), mlam[2 * k + side].copy()
+                vk = index[id(f.adj_var_nodes[side])]
+                f.adj_beliefs[side].eta, f.adj_beliefs[side].lam = eta[vk], lam[vk]
+
+    def _leave_device(self):
+        """Back to the host arithmetic (a host-only method was called): the objects take over the device state."""
+        if self._dev is not None:
+            self._objects_from_device(force=True)
+            self._dev.close()
+            self._dev = None
+        self._dev_tried = False
 
     def energy(self):
+        if self._dev is not None:
+            return self._dev.energy()
         return sum(f.energy() for f in self.factors)
 
     def compute_all_messages(self, local_relin=True):
+        self._leave_device()
         local = self.nonlinear_factors and local_relin
         for f in self.factors:
             if local:
@@ -167,16 +231,22 @@ class FactorGraph:
                 f.compute_messages(self.eta_damping)
 
     def update_all_beliefs(self):
+        if self._dev is not None:
+            self._dev.update_beliefs()
+            self._objects_from_device()
+            return
         for v in self.var_nodes:
             v.update_belief()
 
     def compute_all_factors(self):
+        self._leave_device()          # new linearisation points / factors: the device tables are rebuilt on the next sweep
         for f in self.factors:
             f.compute_factor()
 
     def relinearise_factors(self):
         if not self.nonlinear_factors:
             return
+        self._leave_device()
         for f in self.factors:
             means = f._adj_means()
             if np.linalg.norm(f.linpoint - means) > self.beta and f.iters_since_relin >= self.min_linear_iters:
@@ -187,10 +257,15 @@ class FactorGraph:
                 f.iters_since_relin += 1
 
     def robustify_all_factors(self):
+        self._leave_device()
         for f in self.factors:
             f.robustify_loss()
 
     def synchronous_iteration(self, local_relin=True, robustify=False):
+        if not robustify and not self.nonlinear_factors and self.device_backend() is not None:
+            self._dev.iterate(1)              # gbp/gbp.py:86-92 for a linear graph: messages (graph-level damping), beliefs
+            self._objects_from_device()
+            return
         if robustify:
             self.robustify_all_factors()
         if self.nonlinear_factors and local_relin:
@@ -200,6 +275,9 @@ class FactorGraph:
 
     def joint_distribution_inf(self):
         """Joint information form over all variables (priors + factors at their linearisation points)."""
+        if not self.nonlinear_factors and self.device_backend() is not None:
+            _, _, eta, lam = self._dev.joint_solve(want_sigma=False, want_inf=True)
+            return eta, lam
         dofs = {v.variableID: v.dofs for v in self.var_nodes}
         start, tot = {}, 0
         for v in self.var_nodes:
@@ -217,9 +295,14 @@ class FactorGraph:
         return eta, lam
 
     def joint_distribution_cov(self):
+        if not self.nonlinear_factors and self.device_backend() is not None:
+            mu, sigma, _, _ = self._dev.joint_solve(want_sigma=True)       # dense Cholesky solve + inverse on the device
+            return mu, sigma
         eta, lam = self.joint_distribution_inf()
         sigma = np.linalg.inv(lam)
         return sigma @ eta, sigma
 
     def get_means(self):
+        if self._dev is not None:
+            return self._dev.means().ravel()
         return np.concatenate([v.mu for v in self.var_nodes]) if self.var_nodes else np.array([])

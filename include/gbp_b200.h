@@ -261,6 +261,38 @@ int gbp_bal_copy(const gbp_bal_file* bal, int32_t* cam_id, int32_t* lmk_id, doub
                  double* cam_means /* C x 6 */, double* lmk_means /* L x 3 */, double K4[4]);
 void gbp_bal_close(gbp_bal_file* bal);
 
+/* ---- graphs of pairwise LINEAR factors between variables of equal dimension (the path of ndim_posegraph.py) ---------------
+ * Device counterpart of the generic gbp.FactorGraph(nonlinear_factors=False) (gbp/gbp.py:11-153) for factors that join two
+ * variables of `dim` <= 6 dofs each.  A linear factor never relinearises: Factor.compute_factor (gbp/gbp.py:267-294) is evaluated
+ * once by the caller (the Python callables meas_fn / jac_fn, e.g. gbp/factors/linear_displacement.py:8-14) and passed as
+ *   J   F x dim x 2 dim row-major: jac_fn(x0) = [J_i | J_j], rows beyond the measurement dimension zero (dim(z) <= dim),
+ *   b   F x dim: J x0 + z - meas_fn(x0) (gbp/gbp.py:289), zero-padded,   var  F: gauss_noise_std^2.
+ * Matrices of THIS interface are full dim x dim row-major (the clients hold NumPy matrices).  adj_ptr / adj_msg: for every variable
+ * the incoming messages in VariableNode.adj_factors order (gbp/gbp.py:182-188), an entry = 2 * factor + (0: the variable is the
+ * factor's first, 1: its second).  Messages start at zero (gbp/gbp.py:228); gbp_lin_set_messages uploads the client's. */
+typedef struct gbp_lin_graph* gbp_lin_handle;
+enum { GBP_LIN_BELIEFS = 0, GBP_LIN_MESSAGES = 1 };
+int gbp_lin_create(int32_t dim, int32_t V, int64_t F, const int32_t* var_i, const int32_t* var_j, const double* J, const double* b,
+                   const double* var, const double* prior_eta /* V x dim */, const double* prior_lam /* V x dim x dim */,
+                   const int32_t* adj_ptr /* V + 1 */, const int32_t* adj_msg /* 2 F */, double eta_damping, int device, void* stream,
+                   gbp_lin_handle* out);
+int gbp_lin_destroy(gbp_lin_handle h);
+/* Factor.messages of every factor (gbp/gbp.py:228): eta 2F x dim, lam 2F x dim x dim, message 2 f + side. */
+int gbp_lin_set_messages(gbp_lin_handle h, const double* eta, const double* lam);
+/* FactorGraph.update_all_beliefs (gbp/gbp.py:56-58, 176-198). */
+int gbp_lin_update_beliefs(gbp_lin_handle h);
+/* n x FactorGraph.synchronous_iteration() of a linear graph (gbp/gbp.py:86-92): messages with graph-level eta damping, beliefs. */
+int gbp_lin_iterate(gbp_lin_handle h, int n_iters);
+/* FactorGraph.energy (gbp/gbp.py:36-44). */
+int gbp_lin_energy(gbp_lin_handle h, double* out);
+/* GBP_LIN_BELIEFS: eta V x dim, lam V x dim x dim, mu V x dim (any may be NULL); GBP_LIN_MESSAGES: eta, lam as in set_messages. */
+int gbp_lin_read(gbp_lin_handle h, int what, double* eta, double* lam, double* mu);
+/* FactorGraph.joint_distribution_inf / _cov (gbp/gbp.py:94-144): the joint precision and information vector assembled on the
+ * device (eta_out n, lam_out n x n, n = V dim; may be NULL), mu = Lambda^-1 eta by a dense Cholesky solve on the device and, when
+ * sigma != NULL, sigma = Lambda^-1 (n x n). */
+int gbp_lin_joint_solve(gbp_lin_handle h, double* mu, double* sigma, double* eta_out, double* lam_out);
+int64_t gbp_lin_launch_count(gbp_lin_handle h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -349,7 +349,7 @@ def test_error_behaviour():
     g.close()
 
 
-def _run_reference_script(script, args, timeout=600):
+def _run_reference_script(script, args, timeout=600, env=None):
     """Run an UNMODIFIED script of the staged reference copy (baseline/_ref, put there by __graft_entry__.build()) against
     this engine: `python -m gbp_b200.run <script> ...` only puts gbp_b200/compat (packages gbp / utils / vis) first on sys.path."""
     import os
@@ -360,7 +360,7 @@ def _run_reference_script(script, args, timeout=600):
     if not os.path.exists(path):
         pytest.fail(f"{path} missing: __graft_entry__.build() stages the reference copy (it ships to the GPU box with the tree)")
     import hashlib
-    res = subprocess.run([sys.executable, "-m", "gbp_b200.run", path] + args, cwd=REF_COPY, env=dict(os.environ, PYTHONPATH=ROOT),
+    res = subprocess.run([sys.executable, "-m", "gbp_b200.run", path] + args, cwd=REF_COPY, env=dict(os.environ, PYTHONPATH=ROOT, **(env or {})),
                          capture_output=True, text=True, timeout=timeout)
     assert res.returncode == 0, res.stderr[-2000:]
     return res.stdout, hashlib.sha256(open(path, "rb").read()).hexdigest()
@@ -409,9 +409,10 @@ def test_unmodified_reference_ba_py(data, fixture, extra):
 
 def test_unmodified_reference_ndim_posegraph():
     """BASELINE config 1: ndim_posegraph.py of the staged reference copy, unmodified, on the host graph classes (CPU by
-    contract) -- the check of tests/test_hostgraph.py, here from the shipped copy on the box."""
+    contract; GBP_LINEAR_DEVICE=0 keeps the graph off the GPU engine, which tests/test_lingraph.py covers) -- the check of
+    tests/test_hostgraph.py, here from the shipped copy on the box."""
     G = load_golden("posegraph_n50_d3")
-    out, _ = _run_reference_script("ndim_posegraph.py", ["--n_varnodes", "50", "--dim", "3"])
+    out, _ = _run_reference_script("ndim_posegraph.py", ["--n_varnodes", "50", "--dim", "3"], env={"GBP_LINEAR_DEVICE": "0"})
     lines = [l for l in out.splitlines() if l.startswith("Iteration")]
     assert len(lines) == 50
     assert [float(l.split("Energy")[1].split("//")[0]) for l in lines] == G["energy"].tolist()
