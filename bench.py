@@ -523,19 +523,12 @@ def phase_breakdown(ctx, pg, n=30):
             ev[0].record()
             a.sweep_local(st)                       # sweep_kernel + keyframe partial sums (belief_kernel, keyframe part)
             ev[1].record()
-            if pg.p2p:
-                a.p2p_scatter()
-                ev[2].record()
-                a.landmark_update()
-                ev[3].record()
-                a.p2p_gather_update()
-            else:
-                work = pg.dist.all_gather_into_tensor(pg._gather, a.partial_tensor(), async_op=True)
-                ev[2].record()
-                a.landmark_update()
-                ev[3].record()
-                work.wait()
-                a.apply_gathered(pg._gather, pg.world)
+            work = pg.dist.all_gather_into_tensor(pg._gather, a.partial_tensor(), async_op=True)
+            ev[2].record()
+            a.landmark_update()
+            ev[3].record()
+            work.wait()
+            a.apply_gathered(pg._gather, pg.world)
             ev[4].record()
         torch.cuda.synchronize()
         pg.n_iterations += 1
@@ -543,7 +536,7 @@ def phase_breakdown(ctx, pg, n=30):
             rows.append([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(4)] + [ev[0].elapsed_time(ev[4]) * 1e3])
     med = np.median(np.array(rows), axis=0)
     med = [ctx.max_over_ranks(float(x)) for x in med]
-    names = ["local_sweep_and_keyframe_partial_sums", "exchange_issue" if not pg.p2p else "peer_memory_scatter", "landmark_belief_update",
+    names = ["local_sweep_and_keyframe_partial_sums", "exchange_issue", "landmark_belief_update",
              "exchange_wait_and_keyframe_update", "total_eager"]
     out = dict(zip(names, med))
     out["note"] = "eager launches with CUDA events between the phases, median of %d iterations, max over ranks; the timed solve replays a captured graph without the launch gaps" % n
@@ -566,8 +559,7 @@ def bench_partitioned(ctx, args):
     S = N_ITERS
 
     def build():
-        g = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=ctx.local, dist=dist, torch_stream=ctx.work_stream,
-                               p2p=args.p2p)
+        g = PartitionedBAGraph(prob, CFG, rank=rank, world=world, device=ctx.local, dist=dist, torch_stream=ctx.work_stream)
         return g
 
     def prepare(g):
@@ -603,10 +595,9 @@ def bench_partitioned(ctx, args):
     t_dev = ctx.max_over_ranks(float(np.sum(step_ms)) / 1e3)
     ctx.barrier()
     n_applied = pg.n_iterations
-    breakdown = phase_breakdown(ctx, pg)
-    are, energy, nrel = pg.metrics()
+    are, energy, nrel = pg.metrics()           # the state after exactly S iterations (the breakdown below sweeps on)
     means = pg.get_means()                     # collective: every rank
-    status = pg.adapter.p2p_status() if pg.p2p else None
+    breakdown = phase_breakdown(ctx, pg)
     eng = pg.engine
     total_b, total_b_layout, layout = synth_info(eng, F, Lm, C)
     snap_local = (6 * C + 3 * eng.L) * 8
@@ -676,8 +667,7 @@ def bench_partitioned(ctx, args):
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic BAL graph (gbp_b200/synthetic.py, seed 0): keyframes on a circle, landmarks in a cube, 10 observations per landmark, 2 px noise",
             "config": bench_config(world, args.synth_cams, args.synth_lmks),
-            "engine": {"exchange": "peer-memory kernels (gbp_ba_p2p_*)" if args.p2p else "NCCL all-gather",
-                       "iteration_captured_in_cuda_graph": bool(captured), "layout": layout, "p2p_status": status},
+            "engine": {"exchange": "NCCL all-gather of the keyframe partial sums", "iteration_captured_in_cuda_graph": bool(captured), "layout": layout},
             "ms_per_iteration": 1e3 * t_dev / (args.steps * S), "clocks": clocks,
             "algorithmic_bytes_per_iteration": total_b_layout,
             "frac_of_hbm_peak_whole_iteration_per_gpu": total_b_layout / world / (t_dev / (args.steps * S)) / 1e9 / ctx.hbm_peak,
@@ -824,7 +814,6 @@ def main():
     ap.add_argument("--no-capture", action="store_true", help="multi-GPU: do not capture the iteration in a CUDA graph")
     ap.add_argument("--no-parity-1gpu", action="store_true", help="multi-GPU: skip the single-GPU solve of the whole graph on rank 0")
     ap.add_argument("--no-fr1desk-replicas", action="store_true")
-    ap.add_argument("--p2p", action="store_true", help="multi-GPU: peer-memory exchange kernels instead of the NCCL all-gather")
     ap.add_argument("--synth-cams", type=int, default=1000)
     ap.add_argument("--synth-lmks", type=int, default=1_000_000)
     ap.add_argument("--synth-iters", type=int, default=20)

@@ -12,7 +12,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # gbp_field
 (F_CAM_BELIEF, F_LMK_BELIEF, F_CAM_PRIOR, F_LMK_PRIOR, F_MSG_CAM, F_MSG_LMK, F_LINPOINT, F_ITERS,
@@ -22,7 +22,7 @@ ABI_VERSION = 1
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
-TUNE_PREFETCH_TILES = 3
+TUNE_PREFETCH_TILES, TUNE_BELIEF_LANES = 3, 5
 
 # field -> (index kind, dtype, row width)
 FIELD_SHAPES = {
@@ -47,15 +47,17 @@ class GbpError(RuntimeError):
 class GbpConfig(C.Structure):
     _fields_ = [("gauss_noise_std", C.c_double), ("eta_damping", C.c_double), ("beta", C.c_double),
                 ("Nstds", C.c_double), ("num_undamped_iters", C.c_int32), ("min_linear_iters", C.c_int32),
-                ("loss", C.c_int32), ("tile_edges", C.c_int32), ("lmk_block", C.c_int32), ("kernel_variant", C.c_int32)]
+                ("loss", C.c_int32), ("tile_edges", C.c_int32), ("lmk_block", C.c_int32), ("kernel_variant", C.c_int32),
+                ("lmk_chunks", C.c_int32), ("lmk_chunk_first", C.c_int32), ("lmk_chunks_total", C.c_int32), ("reserved0", C.c_int32),
+                ("lmk_first", C.c_int64), ("lmk_total", C.c_int64)]
 
 
 EXPORTS = [
     "gbp_last_error", "gbp_abi_version", "gbp_device_count", "gbp_ba_create", "gbp_ba_destroy", "gbp_ba_reset", "gbp_ba_sizes", "gbp_ba_layout",
     "gbp_ba_prior_scan", "gbp_ba_generate_priors", "gbp_ba_set_priors", "gbp_ba_scale_priors",
-    "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_p2p_init", "gbp_ba_p2p_attach", "gbp_ba_p2p_scatter", "gbp_ba_p2p_gather_update", "gbp_ba_p2p_status", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
+    "gbp_ba_sweep_local", "gbp_ba_landmark_update", "gbp_ba_cam_update", "gbp_ba_iterate", "gbp_ba_update_beliefs", "gbp_ba_metrics",
     "gbp_ba_snapshot_layout", "gbp_ba_snapshot_async", "gbp_ba_snapshot_wait", "gbp_ba_iterate_snapshot", "gbp_host_alloc", "gbp_host_free", "gbp_ba_read", "gbp_ba_write", "gbp_ba_fill_iters", "gbp_ba_device_ptr", "gbp_ba_set_params",
-    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_plan_create", "gbp_plan_sizes", "gbp_plan_copy", "gbp_plan_destroy", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
+    "gbp_ba_synchronize", "gbp_ba_time_iterations", "gbp_ba_launch_count", "gbp_reprojection_eval", "gbp_plan_create", "gbp_plan_sizes", "gbp_plan_copy", "gbp_plan_chunks", "gbp_plan_destroy", "gbp_bal_open", "gbp_bal_sizes", "gbp_bal_copy", "gbp_bal_close",
     "gbp_cache_configure", "gbp_cache_stats", "gbp_ba_tune",
     "gbp_lin_create", "gbp_lin_destroy", "gbp_lin_set_messages", "gbp_lin_update_beliefs", "gbp_lin_iterate", "gbp_lin_energy", "gbp_lin_read",
     "gbp_lin_joint_solve", "gbp_lin_launch_count",
@@ -91,11 +93,6 @@ def load():
     lib.gbp_ba_sweep_local.argtypes = [vp, C.c_int]
     lib.gbp_ba_landmark_update.argtypes = [vp]
     lib.gbp_ba_cam_update.argtypes = [vp, vp, C.c_int]
-    lib.gbp_ba_p2p_init.argtypes = [vp, C.c_int, C.c_int, vp]
-    lib.gbp_ba_p2p_attach.argtypes = [vp, vp]
-    lib.gbp_ba_p2p_scatter.argtypes = [vp]
-    lib.gbp_ba_p2p_gather_update.argtypes = [vp]
-    lib.gbp_ba_p2p_status.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gbp_ba_iterate.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.gbp_ba_update_beliefs.argtypes = [vp]
     lib.gbp_ba_metrics.argtypes = [vp, dp]
@@ -118,7 +115,8 @@ def load():
     lib.gbp_ba_launch_count.argtypes = [vp]
     lib.gbp_ba_launch_count.restype = C.c_int64
     lib.gbp_reprojection_eval.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp]
-    lib.gbp_plan_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp, vp, C.POINTER(vp)]
+    lib.gbp_plan_create.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int64, vp, vp, C.POINTER(vp)]
+    lib.gbp_plan_chunks.argtypes = [vp, vp, vp]
     lib.gbp_plan_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.gbp_plan_copy.argtypes = [vp] * 10
     lib.gbp_plan_destroy.argtypes = [vp]

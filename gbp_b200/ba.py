@@ -302,7 +302,7 @@ class BAFactorGraph:
     """gbp/gbp_ba.py:12-69 on top of gbp/gbp.py:11-153, device resident."""
 
     def __init__(self, problem: balio.BALProblem, configs: dict, device=0, stream=None, tile_edges=0, lmk_block=0,
-                 kernel_variant=0):
+                 kernel_variant=0, chunks=None):
         self.nonlinear_factors = True
         self._eta_damping = float(configs["eta_damping"])
         self._beta = float(configs["beta"])
@@ -314,7 +314,7 @@ class BAFactorGraph:
         self.K = problem.K
         self._eng = BAEngine(problem.cam_id, problem.lmk_id, problem.z, problem.cam_means, problem.lmk_means,
                              problem.K4, configs, device=device, stream=stream, tile_edges=tile_edges,
-                             lmk_block=lmk_block, kernel_variant=kernel_variant)
+                             lmk_block=lmk_block, kernel_variant=kernel_variant, chunks=chunks)
         e = self._eng
         self.cam_nodes = _LazySeq(e.C, lambda i: FrameVariableNode(self, i))
         self.lmk_nodes = _LazySeq(e.L, lambda i: LandmarkVariableNode(self, i))
@@ -653,8 +653,8 @@ class BAFactorGraph:
         self._eng.close()
 
 
-def create_ba_graph(bal_file, configs, device=0, stream=None, tile_edges=0, lmk_block=0, kernel_variant=0):
+def create_ba_graph(bal_file, configs, device=0, stream=None, tile_edges=0, lmk_block=0, kernel_variant=0, chunks=None):
     """gbp/gbp_ba.py:97-150: build the graph object from a BAL-style file (text or .npz)."""
     problem = bal_file if isinstance(bal_file, balio.BALProblem) else balio.read_bal(bal_file)
     return BAFactorGraph(problem, configs, device=device, stream=stream, tile_edges=tile_edges, lmk_block=lmk_block,
-                         kernel_variant=kernel_variant)
+                         kernel_variant=kernel_variant, chunks=chunks)

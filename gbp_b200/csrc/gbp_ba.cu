@@ -97,24 +97,18 @@ struct gbp_ba_graph {
     int cam_w = CAM_M;   // doubles per stored factor->keyframe message: 27, or 18 with the factored layout (streaming)
     int pf_dist = 0;     // L2 prefetch distance in tiles (streaming build only)
     long long launches = 0;
+    int K_chunks = 1;         // landmark chunks of the keyframe-side sums (gbp_config)
+    int belief_lanes = 0;     // lanes per landmark in belief_kernel: 0 = by graph size (GBP_TUNE_BELIEF_LANES)
 
     // host copies (factor order)
     std::vector<int> h_slot_of_factor, h_file_of_factor, h_adj;
 
     // device state
     DevBuf<Tile> tiles;
-    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
+    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
-
-    // peer-memory exchange (gbp_ba_p2p_*): own buffer, the peers' buffers as mapped here, device table of the bases
-    char* xchg = nullptr;
-    size_t xchg_bytes = 0;
-    std::vector<char*> peer_map;
-    char** peer_tab_dev = nullptr;
-    int p2p_rank = -1, p2p_nranks = 0;
-    long long p2p_flags_off = 0, p2p_slots_off = 0;
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
     Arena arena;
@@ -145,7 +139,8 @@ struct ShapeKey {           // compared bytewise: always built by make_key (zero
     int device, C, L, T, n_tiles, cam_w, pf_dist, streaming, robust, resident;
     long long F, n_slots;
     double cfg_d[4];
-    int cfg_i[6];
+    int cfg_i[10];
+    long long cfg_l[2];
     double K[4];
 };
 
@@ -218,10 +213,6 @@ void cache_put(Shell&& sh) {
 }  // namespace
 
 gbp_ba_graph::~gbp_ba_graph() {
-    for (int r = 0; r < (int)peer_map.size(); ++r)
-        if (peer_map[r] && r != p2p_rank) cudaIpcCloseMemHandle(peer_map[r]);
-    if (peer_tab_dev) cudaFree(peer_tab_dev);
-    if (xchg) cudaFree(xchg);
     if (snap_event) cudaEventDestroy(snap_event);
     // everything else goes back to the shell cache (the stream was synchronised by gbp_ba_destroy; a graph that dies
     // on an error path of gbp_ba_create has nothing in flight that reads the arena after its failed call returned)
@@ -252,6 +243,8 @@ ShapeKey make_key(const gbp_ba_graph* g) {
     k.cfg_d[0] = g->cfg.gauss_noise_std; k.cfg_d[1] = g->cfg.eta_damping; k.cfg_d[2] = g->cfg.beta; k.cfg_d[3] = g->cfg.Nstds;
     k.cfg_i[0] = g->cfg.num_undamped_iters; k.cfg_i[1] = g->cfg.min_linear_iters; k.cfg_i[2] = g->cfg.loss;
     k.cfg_i[3] = g->cfg.tile_edges; k.cfg_i[4] = g->cfg.lmk_block; k.cfg_i[5] = g->cfg.kernel_variant;
+    k.cfg_i[6] = g->cfg.lmk_chunks; k.cfg_i[7] = g->cfg.lmk_chunk_first; k.cfg_i[8] = g->cfg.lmk_chunks_total; k.cfg_i[9] = g->K_chunks;
+    k.cfg_l[0] = g->cfg.lmk_first; k.cfg_l[1] = g->cfg.lmk_total;
     k.K[0] = g->K.fx; k.K[1] = g->K.fy; k.K[2] = g->K.cx; k.K[3] = g->K.cy;
     return k;
 }
@@ -307,9 +300,11 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
+    p.cam_chunk_ptr = g->cam_chunk_ptr.p; p.K = g->K_chunks;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
-    // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds
-    const int lanes = g->L >= 131072 ? 1 : (g->L > 8192 ? 8 : 32);
+    // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds; from ~50 k
+    // landmarks on one thread per landmark wins (125 k landmarks / 1.25 M factors, the per-rank share at 8 GPUs: 45 vs 57 us)
+    const int lanes = g->belief_lanes ? g->belief_lanes : (g->L >= 49152 ? 1 : (g->L > 8192 ? 8 : 32));
     const int per_cta = 128 / lanes;
     const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
@@ -456,6 +451,9 @@ struct GraphPlan {
     std::vector<int> lmk_idx;                                  // [slots] landmark of the edge in that slot (0 in padding)
     std::vector<double> z;                                     // [slots][2] (only when measurements were given)
     std::vector<int> lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
+    int n_chunks = 1;
+    std::vector<int> tile_chunk;                               // [tiles] landmark chunk of every tile
+    std::vector<int> cam_chunk_ptr;                            // [C][chunks + 1] positions in cam_tiles where a keyframe's chunks start
     long long n_slots() const { return (long long)tiles.size() * T; }
 };
 
@@ -471,15 +469,28 @@ int choose_tiling(int tile_edges, long long lmk_block, int L, int64_t F, int* T_
     return GBP_OK;
 }
 
-int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* cam_id, const int32_t* lmk_id, const double* z,
-               GraphPlan* plan) {
+// chunk_bounds: [chunks + 1] landmark boundaries of the chunks (0 ... L); a landmark block never straddles a chunk
+int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_bounds, int C, int L, int64_t F, const int32_t* cam_id,
+               const int32_t* lmk_id, const double* z, GraphPlan* plan) {
     for (int64_t f = 0; f < F; ++f) {
         if (cam_id[f] < 0 || cam_id[f] >= C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)f, cam_id[f]);
         if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
     }
     plan->T = T;
     plan->lblock = lblock;
-    const long long nb = L > 0 ? (L + lblock - 1) / lblock : 1;
+    const int K = std::max<int>(1, (int)chunk_bounds.size() - 1);
+    plan->n_chunks = K;
+    // landmark blocks: every chunk is cut into blocks of lblock landmarks; blocks are numbered chunk by chunk
+    std::vector<int> blk_of_lmk((size_t)L, 0), chunk_of_blk;
+    for (int k = 0; k < K; ++k) {
+        const long long l0 = chunk_bounds.size() > 1 ? chunk_bounds[k] : 0, l1 = chunk_bounds.size() > 1 ? chunk_bounds[k + 1] : L;
+        for (long long b0 = l0; b0 < l1; b0 += lblock) {
+            for (long long l = b0; l < std::min(l1, b0 + lblock); ++l) blk_of_lmk[(size_t)l] = (int)chunk_of_blk.size();
+            chunk_of_blk.push_back(k);
+        }
+    }
+    if (chunk_of_blk.empty()) chunk_of_blk.push_back(0);
+    const long long nb = (long long)chunk_of_blk.size();
 
     // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130)
     std::vector<long long> cam_start((size_t)C + 1, 0);
@@ -499,11 +510,12 @@ int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* 
     // storage order: (landmark block, camera) runs, factor order inside a run
     const size_t nkeys = (size_t)nb * (size_t)std::max(C, 1);
     std::vector<long long> run_start(nkeys + 1, 0);
-    auto key_of = [&](int64_t f) { return (size_t)(plan->adj[2 * f + 1] / lblock) * (size_t)C + (size_t)plan->adj[2 * f]; };
+    auto key_of = [&](int64_t f) { return (size_t)blk_of_lmk[(size_t)plan->adj[2 * f + 1]] * (size_t)C + (size_t)plan->adj[2 * f]; };
     for (int64_t f = 0; f < F; ++f) run_start[key_of(f) + 1]++;
     // tiles per run
     std::vector<Tile>& tiles = plan->tiles;
     tiles.clear();
+    plan->tile_chunk.clear();
     std::vector<long long> run_slot(nkeys, 0);
     {
         long long tcount = 0;
@@ -516,6 +528,7 @@ int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* 
                 t.cam = (int)(k % (size_t)std::max(C, 1));
                 t.count = (int)std::min<long long>(left, T);
                 tiles.push_back(t);
+                plan->tile_chunk.push_back(chunk_of_blk[k / (size_t)std::max(C, 1)]);
                 left -= t.count;
                 ++tcount;
             }
@@ -560,6 +573,36 @@ int plan_graph(int T, long long lblock, int C, int L, int64_t F, const int32_t* 
         std::vector<int> pos(plan->cam_tile_ptr.begin(), plan->cam_tile_ptr.end() - 1);
         for (size_t t = 0; t < tiles.size(); ++t) plan->cam_tiles[(size_t)pos[tiles[t].cam]++] = (int)t;
     }
+    // a keyframe's tiles are listed in tile order = chunk-major: where its chunks start
+    plan->cam_chunk_ptr.assign((size_t)C * (K + 1), 0);
+    for (int c = 0; c < C; ++c) {
+        int* ptr = &plan->cam_chunk_ptr[(size_t)c * (K + 1)];
+        int q = plan->cam_tile_ptr[c];
+        for (int k = 0; k < K; ++k) {
+            ptr[k] = q;
+            while (q < plan->cam_tile_ptr[c + 1] && plan->tile_chunk[(size_t)plan->cam_tiles[(size_t)q]] == k) ++q;
+        }
+        ptr[K] = q;
+        if (q != plan->cam_tile_ptr[c + 1]) return fail(GBP_ERR_INVALID, "internal: tiles of keyframe %d are not in chunk order", c);
+    }
+    return GBP_OK;
+}
+
+// The chunking of a graph: local landmark boundaries of its chunks from the configuration (see gbp_config), 0 = automatic.
+int chunk_bounds_of(const gbp_config* cfg, int L, std::vector<long long>* cb) {
+    int K = cfg ? cfg->lmk_chunks : 0;
+    long long first = 0, total = 0, lmk_first = 0, lmk_total = L;
+    if (K <= 0) {
+        K = L >= 65536 ? 8 : 1;
+        total = K;
+    } else {
+        first = cfg->lmk_chunk_first; total = cfg->lmk_chunks_total; lmk_first = cfg->lmk_first; lmk_total = cfg->lmk_total;
+        if (K > 4096 || first < 0 || total < K || first + K > total || lmk_first < 0 || lmk_total < lmk_first + L)
+            return fail(GBP_ERR_INVALID, "inconsistent landmark chunking (%d chunks from %lld of %lld)", K, first, total);
+    }
+    cb->assign((size_t)K + 1, 0);
+    for (int k = 0; k <= K; ++k) (*cb)[k] = lmk_total * (first + k) / total - lmk_first;
+    if ((*cb)[0] != 0 || (*cb)[K] != L) return fail(GBP_ERR_INVALID, "landmark chunks do not cover this graph's %d landmarks", L);
     return GBP_OK;
 }
 
@@ -620,9 +663,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     g->T = T;
     GraphPlan plan;
     {
-        int rc = plan_graph(T, lblock, C, L, F, cam_id, lmk_id, z, &plan);
+        std::vector<long long> cb;
+        int rc = chunk_bounds_of(cfg, L, &cb);
+        if (rc == GBP_OK) rc = plan_graph(T, lblock, cb, C, L, F, cam_id, lmk_id, z, &plan);
         if (rc != GBP_OK) return rc;
     }
+    g->K_chunks = plan.n_chunks;
     const std::vector<Tile>& tiles = plan.tiles;
     g->n_tiles = (int)tiles.size();
     g->n_slots = plan.n_slots();
@@ -658,12 +704,12 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         g->upload_off = A.used;
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(z, S * 2); ALLOC(slot_of_factor, (size_t)F);
         ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F); ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
-        ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3);
+        ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3); ALLOC(cam_chunk_ptr, plan.cam_chunk_ptr.size());
         g->upload_bytes = A.used - g->upload_off;
         // zero region: everything gbp_ba_reset clears, contiguous -> ONE memset
         zero_off = A.used;
         ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M);
-        ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)C * CAM_M);
+        ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)g->K_chunks * C * CAM_M);
         ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
         zero_end = A.used;
         ALLOC(iters, S); ALLOC(flags, S); ALLOC(linpoint, S * 9); ALLOC(sigma2a, S);
@@ -693,7 +739,8 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
             {plan.z.data(), plan.z.size() * 8, g->z.p}, {g->h_slot_of_factor.data(), g->h_slot_of_factor.size() * 4, g->slot_of_factor.p},
             {plan.lmk_ptr.data(), plan.lmk_ptr.size() * 4, g->lmk_ptr.p}, {plan.lmk_slots.data(), plan.lmk_slots.size() * 4, g->lmk_slots.p},
             {plan.cam_tile_ptr.data(), plan.cam_tile_ptr.size() * 4, g->cam_tile_ptr.p}, {plan.cam_tiles.data(), plan.cam_tiles.size() * 4, g->cam_tiles.p},
-            {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p}};
+            {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p},
+            {plan.cam_chunk_ptr.data(), plan.cam_chunk_ptr.size() * 4, g->cam_chunk_ptr.p}};
         constexpr size_t STAGE_MAX = size_t(32) << 20;   // larger graphs upload table by table (a page-locked block that size costs more than it saves)
         if (g->upload_bytes <= STAGE_MAX) {
             if (g->stage_bytes < g->upload_bytes) {
@@ -805,7 +852,7 @@ int gbp_ba_layout(gbp_handle h, int64_t out[4]) {
     out[0] = h->cam_w;                 // doubles per stored factor->keyframe message: 27 (full) or 18 (factored)
     out[1] = h->pf_dist;               // L2 prefetch distance in tiles (0 = off)
     out[2] = h->streaming ? 2 : 1;     // sweep kernel build in use (gbp_config.kernel_variant after the automatic choice)
-    out[3] = 0;                        // reserved
+    out[3] = h->K_chunks;              // landmark chunks of the keyframe-side sums
     return GBP_OK;
 }
 
@@ -888,99 +935,11 @@ int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {
     CHECK_H(h);
     if (h->C == 0) return GBP_OK;
     const double* src = partials_dev ? partials_dev : h->cam_partial.p;
-    if (!partials_dev) nranks = 1;
-    if (nranks < 1) return fail(GBP_ERR_INVALID, "nranks must be >= 1");
+    if (!partials_dev) nranks = h->K_chunks;
+    if (nranks < 1) return fail(GBP_ERR_INVALID, "the number of partial sums must be >= 1");
     cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p, h->cam_mu.p);
     h->launches++;
     CU(cudaGetLastError());
-    return GBP_OK;
-}
-
-namespace {
-P2PParams p2p_params(gbp_ba_graph* h) {
-    P2PParams p{};
-    p.peers = h->peer_tab_dev; p.mine = h->xchg; p.cam_partial = h->cam_partial.p; p.cam_prior = h->cam_prior.p;
-    p.cam_belief = h->cam_belief.p; p.cam_mu = h->cam_mu.p; p.rank = h->p2p_rank; p.nranks = h->p2p_nranks; p.C = h->C;
-    p.n_cta = (h->C + 3) / 4; p.flags_off = h->p2p_flags_off; p.slots_off = h->p2p_slots_off;
-    return p;
-}
-}  // namespace
-
-int gbp_ba_p2p_init(gbp_handle h, int rank, int nranks, void* ipc_handle_out) {
-    CHECK_H(h);
-    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || !ipc_handle_out) return fail(GBP_ERR_INVALID, "bad rank / nranks / handle pointer");
-    if (h->xchg) return fail(GBP_ERR_STATE, "peer exchange already initialised");
-    static_assert(sizeof(cudaIpcMemHandle_t) == GBP_IPC_HANDLE_BYTES, "GBP_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
-    const size_t n_cta = (size_t)(h->C + 3) / 4;
-    h->p2p_flags_off = sizeof(P2PHeader);
-    const size_t flags = Arena::round_up(2 * (size_t)nranks * std::max<size_t>(n_cta, 1) * sizeof(unsigned int));
-    h->p2p_slots_off = (long long)(h->p2p_flags_off + flags);
-    h->xchg_bytes = (size_t)h->p2p_slots_off + 2 * (size_t)nranks * std::max<size_t>((size_t)h->C, 1) * CAM_M * sizeof(double);
-    CU(cudaMalloc(reinterpret_cast<void**>(&h->xchg), h->xchg_bytes));      // its own allocation: IPC handles name whole allocations
-    CU(cudaMemset(h->xchg, 0, h->xchg_bytes));
-    CU(cudaDeviceSynchronize());
-    cudaIpcMemHandle_t hd;
-    CU(cudaIpcGetMemHandle(&hd, h->xchg));
-    memcpy(ipc_handle_out, &hd, sizeof(hd));
-    h->p2p_rank = rank;
-    h->p2p_nranks = nranks;
-    return GBP_OK;
-}
-
-int gbp_ba_p2p_attach(gbp_handle h, const void* ipc_handles) {
-    CHECK_H(h);
-    if (!h->xchg) return fail(GBP_ERR_STATE, "call gbp_ba_p2p_init first");
-    if (!ipc_handles) return fail(GBP_ERR_INVALID, "null handles");
-    if (!h->peer_map.empty()) return fail(GBP_ERR_STATE, "peers already attached");
-    try {
-        h->peer_map.assign((size_t)h->p2p_nranks, nullptr);
-    } catch (const std::bad_alloc&) {
-        return fail(GBP_ERR_INVALID, "out of host memory");
-    }
-    for (int r = 0; r < h->p2p_nranks; ++r) {
-        if (r == h->p2p_rank) { h->peer_map[r] = h->xchg; continue; }
-        cudaIpcMemHandle_t hd;
-        memcpy(&hd, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof(hd), sizeof(hd));
-        void* ptr = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail(GBP_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (peer access over NVLink needed)", r, cudaGetErrorString(e));
-        h->peer_map[r] = static_cast<char*>(ptr);
-    }
-    CU(cudaMalloc(reinterpret_cast<void**>(&h->peer_tab_dev), (size_t)h->p2p_nranks * sizeof(char*)));
-    CU(cudaMemcpy(h->peer_tab_dev, h->peer_map.data(), (size_t)h->p2p_nranks * sizeof(char*), cudaMemcpyHostToDevice));
-    return GBP_OK;
-}
-
-int gbp_ba_p2p_scatter(gbp_handle h) {
-    CHECK_H(h);
-    if (!h->peer_tab_dev) return fail(GBP_ERR_STATE, "peer exchange not attached");
-    if (h->C == 0) return GBP_OK;
-    p2p_scatter_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(p2p_params(h));
-    h->launches++;
-    CU(cudaGetLastError());
-    return GBP_OK;
-}
-
-int gbp_ba_p2p_gather_update(gbp_handle h) {
-    CHECK_H(h);
-    if (!h->peer_tab_dev) return fail(GBP_ERR_STATE, "peer exchange not attached");
-    if (h->C == 0) return GBP_OK;
-    p2p_gather_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(p2p_params(h));
-    h->launches++;
-    CU(cudaGetLastError());
-    return GBP_OK;
-}
-
-int gbp_ba_p2p_status(gbp_handle h, int64_t out[2]) {
-    CHECK_H(h);
-    if (!out) return fail(GBP_ERR_INVALID, "null out");
-    out[0] = out[1] = 0;
-    if (!h->xchg) return GBP_OK;
-    P2PHeader hd;
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(&hd, h->xchg, sizeof(hd), cudaMemcpyDeviceToHost));
-    out[0] = hd.epoch;       // exchanges completed
-    out[1] = hd.timeouts;    // flag waits that gave up (a peer died or never launched its scatter)
     return GBP_OK;
 }
 
@@ -1131,7 +1090,7 @@ int gbp_ba_read(gbp_handle h, int field, void* host_dst, size_t bytes) {
     CHECK_H(h);
     FieldInfo fi;
     if (!field_info(field, &fi)) return fail(GBP_ERR_INVALID, "unknown field %d", field);
-    const long long rows = fi.indexed == 0 ? h->C : fi.indexed == 1 ? h->L : h->F;
+    const long long rows = field == GBP_F_CAM_PARTIAL ? (long long)h->K_chunks * h->C : fi.indexed == 0 ? h->C : fi.indexed == 1 ? h->L : h->F;
     const size_t need = (size_t)rows * fi.words * 4;
     if (bytes != need) return fail(GBP_ERR_INVALID, "field %d: expected %zu bytes, got %zu", field, need, bytes);
     if (need == 0) return GBP_OK;
@@ -1218,7 +1177,7 @@ int gbp_ba_device_ptr(gbp_handle h, int field, void** dev_ptr, size_t* bytes) {
     FieldInfo fi;
     if (!field_info(field, &fi) || fi.indexed == 2) return fail(GBP_ERR_INVALID, "field %d has no stable device layout", field);
     *dev_ptr = field_dev_ptr(h, field);
-    if (bytes) *bytes = (size_t)(fi.indexed == 0 ? h->C : h->L) * fi.words * 4;
+    if (bytes) *bytes = (size_t)(fi.indexed == 0 ? h->C : h->L) * fi.words * 4 * (field == GBP_F_CAM_PARTIAL ? (size_t)h->K_chunks : 1);
     return GBP_OK;
 }
 
@@ -1243,6 +1202,15 @@ int gbp_ba_synchronize(gbp_handle h) {
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value) {
     CHECK_H(h);
     switch (knob) {
+        case GBP_TUNE_BELIEF_LANES:
+            if (value != 0 && value != 1 && value != 8 && value != 32) return fail(GBP_ERR_INVALID, "lanes per landmark: 0 (automatic), 1, 8 or 32");
+            CU(cudaStreamSynchronize(h->stream));
+            h->belief_lanes = (int)value;
+            for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+            h->graphs.clear();
+            for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
+            h->snap_graphs.clear();
+            return GBP_OK;
         case GBP_TUNE_PREFETCH_TILES:
             if (value < 0) return fail(GBP_ERR_INVALID, "prefetch distance must be >= 0");
             CU(cudaStreamSynchronize(h->stream));
@@ -1349,7 +1317,7 @@ struct gbp_plan_s {
     int64_t F = 0;
 };
 
-int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
+int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, const int64_t* chunking, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
                     const int32_t* lmk_id, gbp_plan* out) {
     if (!out) return fail(GBP_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -1361,7 +1329,14 @@ int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, int32_t C, int32_t L,
         int T = 32;
         long long lblock = 1;
         int rc = choose_tiling(tile_edges, lmk_block, L, F, &T, &lblock);
-        if (rc == GBP_OK) rc = plan_graph(T, lblock, C, L, F, cam_id, lmk_id, nullptr, &p->plan);
+        std::vector<long long> cb;
+        gbp_config cc{};
+        if (chunking) {
+            cc.lmk_chunks = (int32_t)chunking[0]; cc.lmk_chunk_first = (int32_t)chunking[1]; cc.lmk_chunks_total = (int32_t)chunking[2];
+            cc.lmk_first = chunking[3]; cc.lmk_total = chunking[4];
+        }
+        if (rc == GBP_OK) rc = chunk_bounds_of(&cc, L, &cb);
+        if (rc == GBP_OK) rc = plan_graph(T, lblock, cb, C, L, F, cam_id, lmk_id, nullptr, &p->plan);
         if (rc != GBP_OK) return rc;
         *out = p.release();
         return GBP_OK;
@@ -1385,6 +1360,14 @@ int gbp_plan_copy(gbp_plan p, int32_t* tiles, int32_t* slot_of_factor, int32_t* 
     cp(slot_of_factor, g.slot_of_factor); cp(file_of_factor, g.file_of_factor); cp(adj, g.adj); cp(lmk_idx, g.lmk_idx);
     cp(lmk_ptr, g.lmk_ptr); cp(lmk_slots, g.lmk_slots); cp(cam_tile_ptr, g.cam_tile_ptr); cp(cam_tiles, g.cam_tiles);
     return GBP_OK;
+}
+
+int gbp_plan_chunks(gbp_plan p, int32_t* tile_chunk, int32_t* cam_chunk_ptr) {
+    if (!p) return 0;
+    const GraphPlan& g = p->plan;
+    if (tile_chunk && !g.tile_chunk.empty()) memcpy(tile_chunk, g.tile_chunk.data(), g.tile_chunk.size() * sizeof(int));
+    if (cam_chunk_ptr && !g.cam_chunk_ptr.empty()) memcpy(cam_chunk_ptr, g.cam_chunk_ptr.data(), g.cam_chunk_ptr.size() * sizeof(int));
+    return g.n_chunks;
 }
 
 void gbp_plan_destroy(gbp_plan p) { delete p; }

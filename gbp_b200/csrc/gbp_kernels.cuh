@@ -292,7 +292,9 @@ struct BeliefParams {
     const int* cam_tiles;    // [n_tiles]
     const double* cam_prior;
     double* cam_belief;
-    double* cam_partial;     // [C][27]
+    double* cam_partial;     // [K][C][27]  sums of the factor->keyframe messages per landmark chunk
+    const int* cam_chunk_ptr;   // [C][K + 1] positions in cam_tiles where the chunks of a keyframe start
+    int K;                   // landmark chunks
     double* cam_mu;          // [C][6]  compact copy of the means (snapshot region)
     double* lmk_mu;          // [L][3]
     int L, C, finalise;
@@ -342,19 +344,25 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
         const int c = (int)blockIdx.x * 4 + (threadIdx.x >> 5);
         const int lane = threadIdx.x & 31;
         if (c >= p.C) return;
+        // per landmark chunk: tile sums in tile order; then the chunk sums in chunk order (the same association on every number of
+        // GPUs: a rank holds whole chunks), then the prior
         double acc = 0.0;
         if (lane < CAM_M) {
-            const int t0 = p.cam_tile_ptr[c], t1 = p.cam_tile_ptr[c + 1];
-            int q = t0;
-            for (; q + 8 <= t1; q += 8) {          // 8 independent loads in flight, added in tile order
-                double v[8];
+            for (int k = 0; k < p.K; ++k) {
+                const int t0 = p.cam_chunk_ptr[c * (p.K + 1) + k], t1 = p.cam_chunk_ptr[c * (p.K + 1) + k + 1];
+                double part = 0.0;
+                int q = t0;
+                for (; q + 8 <= t1; q += 8) {          // 8 independent loads in flight, added in tile order
+                    double v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = p.tile_partial[(long long)p.cam_tiles[q + k] * CAM_M + lane];
+                    for (int u = 0; u < 8; ++u) v[u] = p.tile_partial[(long long)p.cam_tiles[q + u] * CAM_M + lane];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc += v[k];
+                    for (int u = 0; u < 8; ++u) part += v[u];
+                }
+                for (; q < t1; ++q) part += p.tile_partial[(long long)p.cam_tiles[q] * CAM_M + lane];
+                p.cam_partial[((long long)k * p.C + c) * CAM_M + lane] = part;
+                acc = k == 0 ? part : acc + part;
             }
-            for (; q < t1; ++q) acc += p.tile_partial[(long long)p.cam_tiles[q] * CAM_M + lane];
-            p.cam_partial[(long long)c * CAM_M + lane] = acc;
             acc += p.cam_prior[(long long)c * CAM_M + lane];
         }
         if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6);
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     }
 }
 
-// keyframe beliefs from gathered per-rank partial sums (multi-GPU): prior + sum_r partial[r]
+// keyframe beliefs from the gathered chunk sums (multi-GPU): chunk sums in chunk order, then the prior -- the association of belief_kernel
 __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restrict__ partials, int nranks, int C,
                                                          const double* __restrict__ cam_prior,
                                                          double* __restrict__ cam_belief, double* __restrict__ cam_mu) {
@@ -422,109 +430,15 @@ __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restric
     if (c >= C) return;
     double acc = 0.0;
     if (lane < CAM_M) {
-        for (int r = 0; r < nranks; ++r) acc += partials[((long long)r * C + c) * CAM_M + lane];
+        for (int r = 0; r < nranks; ++r) {
+            const double part = partials[((long long)r * C + c) * CAM_M + lane];
+            acc = r == 0 ? part : acc + part;
+        }
         acc += cam_prior[(long long)c * CAM_M + lane];
     }
     cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B, cam_mu + (long long)c * 6);
 }
 
-
-// ----------------------------------------------------------------------------------------
-// Peer-memory exchange of the keyframe partial sums (multi-GPU, one process per GPU; opt-in, see gbp_ba_p2p_*).
-// Replaces [all-gather of C x 27 doubles -> cam_update_kernel] by two kernels that talk through NVLink directly:
-//   p2p_scatter_kernel        every rank writes its partial sums into slot [my rank] of EVERY rank's exchange buffer
-//                             (plain stores to peer memory), fences, then raises flag [my rank][CTA] in that buffer;
-//   p2p_gather_update_kernel  CTA b waits until all ranks raised flag [.][b] for this epoch, then adds prior + the
-//                             partial sums in rank order (bit-identical beliefs on every rank) and finalises its 4
-//                             keyframes.  The landmark belief update runs between the two and hides the transfer.
-// No grid-wide or cross-rank barrier: CTA b only depends on CTA b of the other ranks.  Slots and flags are double
-// buffered by epoch parity: a rank can be at most one exchange ahead of the slowest one (it needs everybody's sums of
-// epoch n to finish n), so epoch n + 1 never overwrites data somebody still reads.  A wait gives up after ~2 s instead of
-// hanging the GPU when a peer died: it counts a timeout (gbp_ba_p2p_status) and the keyframes of that CTA get NaN beliefs,
-// so a lost exchange can never pass as a result.
-// ----------------------------------------------------------------------------------------
-struct P2PHeader {
-    unsigned int epoch;      // exchanges completed so far (advanced by the last CTA of the gather kernel)
-    unsigned int done;       // CTA ticket of the gather kernel
-    unsigned int timeouts;   // flag waits that gave up
-    unsigned int pad[61];
-};
-struct P2PParams {
-    char* const* peers;      // [nranks] base of every rank's exchange buffer as mapped into THIS process
-    char* mine;              // == peers[rank]
-    const double* cam_partial;
-    const double* cam_prior;
-    double* cam_belief;
-    double* cam_mu;
-    int rank, nranks, C, n_cta;
-    long long flags_off, slots_off;   // byte offsets inside an exchange buffer
-};
-__device__ __forceinline__ unsigned int* p2p_flag(char* base, const P2PParams& p, int set, int src, int cta) {
-    return reinterpret_cast<unsigned int*>(base + p.flags_off) + ((long long)set * p.nranks + src) * p.n_cta + cta;
-}
-__device__ __forceinline__ double* p2p_slot(char* base, const P2PParams& p, int set, int src, int c) {
-    return reinterpret_cast<double*>(base + p.slots_off) + (((long long)set * p.nranks + src) * p.C + c) * CAM_M;
-}
-
-__global__ void __launch_bounds__(128) p2p_scatter_kernel(const P2PParams p) {
-    const unsigned int epoch = reinterpret_cast<const volatile P2PHeader*>(p.mine)->epoch + 1;
-    const int set = (int)(epoch & 1u);
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c < p.C && lane < CAM_M) {
-        const double v = p.cam_partial[(long long)c * CAM_M + lane];
-        for (int r = 0; r < p.nranks; ++r) p2p_slot(p.peers[r], p, set, p.rank, c)[lane] = v;
-    }
-    __threadfence_system();          // my stores are visible system-wide before the flag is
-    __syncthreads();
-    if ((int)threadIdx.x < p.nranks) {
-        unsigned int* f = p2p_flag(p.peers[threadIdx.x], p, set, p.rank, blockIdx.x);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-    }
-}
-
-__global__ void __launch_bounds__(128) p2p_gather_update_kernel(const P2PParams p) {
-    volatile P2PHeader* hdr = reinterpret_cast<volatile P2PHeader*>(p.mine);
-    const unsigned int epoch = hdr->epoch + 1;
-    const int set = (int)(epoch & 1u);
-    __shared__ int s_timed_out;
-    if (threadIdx.x == 0) s_timed_out = 0;
-    __syncthreads();
-    if ((int)threadIdx.x < p.nranks) {
-        const unsigned int* f = p2p_flag(p.mine, p, set, threadIdx.x, blockIdx.x);
-        const long long t0 = clock64();
-        unsigned int v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v == epoch) break;
-            if (clock64() - t0 > 4000000000LL) {          // ~2 s: a peer is gone; do not hang the GPU
-                atomicAdd(const_cast<unsigned int*>(&hdr->timeouts), 1u);
-                s_timed_out = 1;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c < p.C) {
-        double acc = 0.0;
-        if (lane < CAM_M) {
-            for (int r = 0; r < p.nranks; ++r) acc += __ldcv(p2p_slot(p.mine, p, set, r, c) + lane);   // rank order
-            acc += p.cam_prior[(long long)c * CAM_M + lane];
-            if (s_timed_out) acc = __longlong_as_double(0x7ff8000000000000LL);   // a peer never delivered: poison, do not guess
-        }
-        cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(const_cast<unsigned int*>(&hdr->done), 1u);
-        if (t == gridDim.x - 1) {        // every CTA has read `epoch`: advance it for the next exchange
-            hdr->done = 0;
-            hdr->epoch = epoch;
-            __threadfence();
-        }
-    }
-}
 
 // ----------------------------------------------------------------------------------------
 // K5: BAFactorGraph.are / FactorGraph.energy / relinearisation count

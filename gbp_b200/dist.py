@@ -5,13 +5,18 @@ are local) and the boundary variables are the keyframes, replicated on every ran
 synchronous iteration each rank runs the sweep over its own edges, reduces its local
 factor->keyframe messages to one partial (eta, Lambda) sum per keyframe (C x 27 doubles), and the
 ranks exchange those partial sums with ONE all-gather (NCCL over NVLink / NVSwitch; gloo in the
-CPU tests); every rank then adds prior + the partials in rank order, so the keyframe beliefs are
+CPU tests); every rank then adds the partials in rank order and the prior, so the keyframe beliefs are
 bit-identical everywhere.  ARE / energy need a 3-scalar all-reduce only when the client asks.
 
-`p2p=True`: the exchange without a collective call.  Every rank writes its partial sums straight into the other
-ranks' exchange buffers over NVLink (CUDA IPC mappings of one small buffer per rank) and raises per-CTA flags
-there; the keyframe update kernel waits on the flags of its own buffer (`gbp_ba_p2p_*`, kernels
-`p2p_scatter_kernel` / `p2p_gather_update_kernel`).  Same rank-ordered sum, so the same bits.
+Bit-identical across the NUMBER of GPUs as well: the engine forms the keyframe-side sums per landmark CHUNK (gbp_config:
+8 chunks of consecutive landmarks from 65536 landmarks on) and adds the chunk sums in chunk order; a rank holds whole chunks of
+that global chunking (its partial "sum" is its chunk sums, K / world x C x 27 doubles) and lays out exactly the tiles the
+single-GPU plan has for them (tile size, landmark blocks and kernel build are chosen from the GLOBAL sizes).  So 1, 2, 4 and 8
+GPUs run the same floating-point operations in the same order and produce the same bits.
+
+(A collective-free exchange -- every rank storing its partial sums into the other ranks' buffers over NVLink through CUDA IPC
+mappings, per-CTA flags -- was built and run on 2 and 8 GPUs in round 2: same bits, same speed as the all-gather within 1 %
+(0.2143 vs 0.2130 ms per iteration at 8 GPUs), so it was removed again; profiles/r2e_bench_n8_*.json.)
 
 Streams: with world > 1 the engine's kernels and the collective must be ordered on ONE stream.  The graph takes a
 single `torch_stream` (a torch.cuda.Stream; created here when omitted), hands its raw handle to the engine and
@@ -37,6 +42,20 @@ def landmark_partition(n_lmks: int, world: int):
     return [(n_lmks * r) // world for r in range(world + 1)]
 
 
+def global_layout(prob: BALProblem, world: int):
+    """Engine layout choices made from the GLOBAL sizes, so that every rank lays out its share exactly like the single-GPU plan
+    (the rules of choose_tiling / chunk_bounds_of / the streaming switch in gbp_ba.cu): tile size, landmark block, kernel build,
+    number of landmark chunks (a multiple of world)."""
+    F, Lm = prob.n_edges, prob.n_points
+    T = 64 if F >= 64 * 148 * 6 else 32
+    lblock = max(Lm, 1) if Lm * 96 <= (24 << 20) else 262144
+    k_auto = 8 if Lm >= 65536 else 1
+    k_total = k_auto if k_auto % world == 0 else world
+    variant = 2 if (F // T > 8192 and T <= 64) else 1
+    lanes = 1 if Lm >= 49152 else (8 if Lm > 8192 else 32)         # belief_kernel: the lane count fixes the landmark summation order
+    return dict(tile_edges=T, lmk_block=lblock, kernel_variant=variant, belief_lanes=lanes), k_total
+
+
 def local_problem(prob: BALProblem, rank: int, world: int):
     """The sub-problem of one rank: all keyframes, its landmark block, the measurements of those landmarks
     (file order preserved).  Returns (BALProblem with local landmark ids, global index of each local measurement)."""
@@ -57,13 +76,16 @@ class _DevArray:
 class CudaEngineAdapter:
     """The CUDA engine seen through the four operations the exchange layer needs."""
 
-    def __init__(self, sub: BALProblem, configs, device, stream, **kw):
+    def __init__(self, sub: BALProblem, configs, device, stream, belief_lanes=0, **kw):
         import torch
         from .engine import BAEngine
         self.eng = BAEngine(sub.cam_id, sub.lmk_id, sub.z, sub.cam_means, sub.lmk_means, sub.K4, configs, device=device,
                             stream=stream, **kw)
+        if belief_lanes:
+            self.eng.tune(L.TUNE_BELIEF_LANES, belief_lanes)
         ptr, nbytes = self.eng.device_ptr(L.F_CAM_PARTIAL)
         self._partial = torch.as_tensor(_DevArray(ptr, nbytes // 8), device=f"cuda:{device}")
+        self.partials_per_rank = self.eng.lmk_chunks          # chunk sums this rank contributes to the exchange
         self._torch = torch
 
     C = property(lambda self: self.eng.C)
@@ -92,24 +114,7 @@ class CudaEngineAdapter:
         return self._torch.empty(world * self._partial.numel(), dtype=self._torch.float64, device=self._partial.device)
 
     def apply_gathered(self, gathered, world):
-        self.eng.cam_update(gathered.data_ptr(), world)
-
-    # ---- peer-memory exchange (opt-in)
-    def p2p_setup(self, rank, world, dist):
-        handle = self.eng.p2p_init(rank, world)
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)        # 64-byte CUDA IPC handles, rank order
-        self.eng.p2p_attach(handles)
-        dist.barrier()                                  # everybody mapped everybody before the first store
-
-    def p2p_scatter(self):
-        self.eng.p2p_scatter()
-
-    def p2p_gather_update(self):
-        self.eng.p2p_gather_update()
-
-    def p2p_status(self):
-        return self.eng.p2p_status()
+        self.eng.cam_update(gathered.data_ptr(), world * self.partials_per_rank)
 
     def iterate_single(self, robustify, local_relin):
         self.eng.iterate(1, robustify=robustify, local_relin=local_relin)
@@ -141,7 +146,7 @@ class PartitionedBAGraph:
     """`synchronous_iteration` / `generate_priors_var` / `are` / `energy` over a landmark-partitioned graph."""
 
     def __init__(self, prob: BALProblem, configs, rank=0, world=1, device=0, stream=None, dist=None,
-                 engine_factory=None, torch_stream=None, p2p=False, **engine_kw):
+                 engine_factory=None, torch_stream=None, **engine_kw):
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs an initialised torch.distributed module")
         if engine_factory is None and world > 1:
@@ -160,14 +165,15 @@ class PartitionedBAGraph:
         self.n_iterations = 0        # synchronous iterations applied to the state since creation / reset
         self.F_total, self.L_total, self.C = prob.n_edges, prob.n_points, prob.n_keyframes
         sub, self.local_measurements, self.lmk_range = local_problem(prob, rank, world)
+        if engine_factory is None and world > 1:
+            layout, k_total = global_layout(prob, world)
+            k_local = k_total // world
+            for k, v in layout.items():
+                engine_kw.setdefault(k, v)
+            engine_kw.setdefault("chunks", (k_local, rank * k_local, k_total, self.lmk_range[0], prob.n_points))
         factory = engine_factory or (lambda s, c: CudaEngineAdapter(s, c, device, stream, **engine_kw))
         self.adapter = factory(sub, configs)
         self._gather = self.adapter.new_gather_buffer(world) if world > 1 else None
-        self.p2p = bool(p2p) and world > 1
-        if self.p2p:
-            if not hasattr(self.adapter, "p2p_setup"):
-                raise ValueError("this engine has no peer-memory exchange (p2p=True needs the CUDA engine)")
-            self.adapter.p2p_setup(rank, world, dist)
         self._graphs = {}        # stages -> captured CUDA graph of [local sweep, all-gather, keyframe update]
         self._torch_stream = engine_kw_stream
 
@@ -180,11 +186,6 @@ class PartitionedBAGraph:
         """keyframe partial sums -> all ranks (one all-gather); the landmark beliefs, which need no communication, are
         updated on the compute stream while the collective is in flight; then prior + partials in rank order."""
         a = self.adapter
-        if self.p2p:
-            a.p2p_scatter()             # partial sums -> every peer's buffer (stores over NVLink) + flags
-            a.landmark_update()         # overlaps the transfer
-            a.p2p_gather_update()       # waits on this rank's flags; prior + sums in rank order
-            return
         with self._stream_ctx():
             work = self.dist.all_gather_into_tensor(self._gather, a.partial_tensor(), async_op=True)
             a.landmark_update()
@@ -254,9 +255,8 @@ class PartitionedBAGraph:
             return True
         # NCCL sets up its channels on the first collective, which must happen outside the capture: gather the current
         # partial sums into the scratch buffer once (touches no state of the solve)
-        if not self.p2p:
-            with self._stream_ctx():
-                self.dist.all_gather_into_tensor(self._gather, self.adapter.partial_tensor())
+        with self._stream_ctx():
+            self.dist.all_gather_into_tensor(self._gather, self.adapter.partial_tensor())
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._torch_stream, capture_error_mode="thread_local"):
@@ -275,7 +275,6 @@ class PartitionedBAGraph:
 
     def metrics(self):
         """(ARE, energy, number of factors with iters_since_relin == 0) over the WHOLE graph."""
-        self._check_exchange()
         m = self.adapter.metrics()
         if self.world > 1:
             import torch
@@ -290,18 +289,8 @@ class PartitionedBAGraph:
     def energy(self):
         return self.metrics()[1]
 
-    def _check_exchange(self):
-        """A peer-memory exchange that timed out (a peer died or never launched) poisons the keyframe beliefs with NaN on the
-        device; turn it into an exception as soon as the client looks at results."""
-        if self.p2p:
-            done, timeouts = self.adapter.p2p_status()
-            if timeouts:
-                raise RuntimeError(f"rank {self.rank}: {timeouts} peer-memory exchange wait(s) timed out after {done} exchanges; "
-                                   "the keyframe beliefs are invalid")
-
     def get_means(self):
         """All belief means in variable order (keyframes, then landmarks) on every rank."""
-        self._check_exchange()
         cam = self.adapter.cam_means().ravel()
         lmk = self.adapter.lmk_means()
         if self.world > 1:
@@ -316,8 +305,4 @@ class PartitionedBAGraph:
             import torch
             torch.cuda.synchronize()
             self._graphs.clear()
-        if self.p2p:
-            import torch
-            torch.cuda.synchronize()
-            self.dist.barrier()          # nobody still writes into a buffer that is about to be freed
         self.adapter.close()

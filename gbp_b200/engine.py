@@ -33,7 +33,9 @@ def pack_sym(full):
 
 class BAEngine:
     def __init__(self, cam_id, lmk_id, z, cam_mu0, lmk_mu0, K4, configs, device=0, stream=None,
-                 tile_edges=0, lmk_block=0, kernel_variant=0):
+                 tile_edges=0, lmk_block=0, kernel_variant=0, chunks=None):
+        """chunks: None = automatic chunking of this graph, or (lmk_chunks, lmk_chunk_first, lmk_chunks_total, lmk_first, lmk_total):
+        this graph's share of a global landmark chunking (multi-GPU, see gbp_config in include/gbp_b200.h)."""
         lib = L.load()
         self._lib = lib
         self._h = None
@@ -50,7 +52,8 @@ class BAEngine:
             raise ValueError(f"unknown loss {loss!r} (None, 'huber' or 'constant')")
         cfg = L.GbpConfig(float(configs["gauss_noise_std"]), float(configs["eta_damping"]), float(configs["beta"]),
                           float(configs.get("Nstds", 3.0)), int(configs["num_undamped_iters"]),
-                          int(configs["min_linear_iters"]), L.LOSS_CODES[loss], int(tile_edges), int(lmk_block), int(kernel_variant))
+                          int(configs["min_linear_iters"]), L.LOSS_CODES[loss], int(tile_edges), int(lmk_block), int(kernel_variant),
+                          *([0, 0, 0, 0, 0, 0] if chunks is None else [int(chunks[0]), int(chunks[1]), int(chunks[2]), 0, int(chunks[3]), int(chunks[4])]))
         self.cfg = cfg
         h = C.c_void_p()
         L.check(lib.gbp_ba_create(C.byref(cfg), len(cam_mu0), len(lmk_mu0), len(cam_id), L.ptr(cam_id), L.ptr(lmk_id),
@@ -64,6 +67,7 @@ class BAEngine:
         L.check(lib.gbp_ba_layout(h, lay))
         # doubles per stored factor->keyframe message (27 full / 18 factored), L2 prefetch distance, sweep kernel build
         self.msg_cam_width, self.prefetch_tiles, self.sweep_variant = int(lay[0]), int(lay[1]), int(lay[2])
+        self.lmk_chunks = int(lay[3])      # landmark chunks of the keyframe-side sums (GBP_F_CAM_PARTIAL holds lmk_chunks x C rows)
         self.K4 = K4
         self.device = int(device)
 
@@ -116,29 +120,6 @@ class BAEngine:
     def cam_update(self, partials_dev_ptr=None, nranks=1):
         L.check(self._lib.gbp_ba_cam_update(self._h, C.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
                                             int(nranks)))
-
-    # ------------------------------------------------------------------ peer-memory exchange (multi-GPU, opt-in)
-    def p2p_init(self, rank, nranks):
-        """Allocate this rank's exchange buffer; returns its CUDA IPC handle (bytes) for the other ranks."""
-        buf = C.create_string_buffer(64)
-        L.check(self._lib.gbp_ba_p2p_init(self._h, int(rank), int(nranks), buf))
-        return buf.raw
-
-    def p2p_attach(self, handles):
-        """`handles`: the IPC handles of all ranks in rank order (own entry ignored)."""
-        blob = b"".join(handles)
-        L.check(self._lib.gbp_ba_p2p_attach(self._h, C.c_char_p(blob)))
-
-    def p2p_scatter(self):
-        L.check(self._lib.gbp_ba_p2p_scatter(self._h))
-
-    def p2p_gather_update(self):
-        L.check(self._lib.gbp_ba_p2p_gather_update(self._h))
-
-    def p2p_status(self):
-        out = (C.c_int64 * 2)()
-        L.check(self._lib.gbp_ba_p2p_status(self._h, out))
-        return int(out[0]), int(out[1])
 
     def iterate(self, n_iters=1, robustify=False, local_relin=True):
         L.check(self._lib.gbp_ba_iterate(self._h, int(n_iters), int(bool(robustify)), int(bool(local_relin))))
@@ -196,7 +177,7 @@ class BAEngine:
 
     def read(self, field, out=None):
         kind, dt, w = L.FIELD_SHAPES[field]
-        n = self._rows(kind)
+        n = self._rows(kind) * (self.lmk_chunks if field == L.F_CAM_PARTIAL else 1)      # chunk sums: chunks x C rows
         if out is None:
             out = L.pinned_empty((n, w), dt)
         assert out.dtype == dt and out.size == n * w and out.flags.c_contiguous
@@ -223,17 +204,21 @@ def reprojection_eval(x, K4, device=0):
     return h, J.reshape(-1, 2, 9)
 
 
-def compile_plan(cam_id, lmk_id, n_keyframes, n_landmarks, tile_edges=0, lmk_block=0):
+def compile_plan(cam_id, lmk_id, n_keyframes, n_landmarks, tile_edges=0, lmk_block=0, chunks=None):
     """The engine's storage order for a measurement list, from the native host graph compiler (`gbp_plan_*`; pure host
     code, no GPU needed): dict with T, tiles [(keyframe, count)], slot_of_factor, file_of_factor, adj, lmk_idx (per slot),
-    lmk_ptr / lmk_slots (CSR by landmark over slots), cam_tile_ptr / cam_tiles (CSR by keyframe over tiles)."""
+    lmk_ptr / lmk_slots (CSR by landmark over slots), cam_tile_ptr / cam_tiles (CSR by keyframe over tiles), n_chunks,
+    tile_chunk (landmark chunk of every tile) and cam_chunk_ptr (per keyframe where its chunks start in cam_tiles)."""
     lib = L.load()
     cam_id = np.ascontiguousarray(cam_id, dtype=np.int32)
     lmk_id = np.ascontiguousarray(lmk_id, dtype=np.int32)
     if len(cam_id) != len(lmk_id):
         raise ValueError("cam_id and lmk_id must have one entry per measurement")
     p = C.c_void_p()
-    L.check(lib.gbp_plan_create(int(tile_edges), int(lmk_block), int(n_keyframes), int(n_landmarks), len(cam_id),
+    if isinstance(chunks, int):
+        chunks = (chunks, 0, chunks, 0, n_landmarks)
+    ch = None if chunks is None else np.array(chunks, dtype=np.int64)
+    L.check(lib.gbp_plan_create(int(tile_edges), int(lmk_block), L.ptr(ch), int(n_keyframes), int(n_landmarks), len(cam_id),
                                 L.ptr(cam_id), L.ptr(lmk_id), C.byref(p)))
     try:
         sizes = (C.c_int64 * 6)()
@@ -246,6 +231,10 @@ def compile_plan(cam_id, lmk_id, n_keyframes, n_landmarks, tile_edges=0, lmk_blo
                "cam_tile_ptr": np.zeros(nc + 1, np.int32), "cam_tiles": np.zeros(n_tiles, np.int32)}
         L.check(lib.gbp_plan_copy(p, *[L.ptr(out[k]) for k in ("tiles", "slot_of_factor", "file_of_factor", "adj", "lmk_idx",
                                                               "lmk_ptr", "lmk_slots", "cam_tile_ptr", "cam_tiles")]))
+        out["n_chunks"] = int(lib.gbp_plan_chunks(p, None, None))
+        out["tile_chunk"] = np.zeros(n_tiles, np.int32)
+        out["cam_chunk_ptr"] = np.zeros((nc, out["n_chunks"] + 1), np.int32)
+        lib.gbp_plan_chunks(p, L.ptr(out["tile_chunk"]), L.ptr(out["cam_chunk_ptr"]))
         return out
     finally:
         lib.gbp_plan_destroy(p)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GBP_B200_ABI_VERSION 1
+#define GBP_B200_ABI_VERSION 2
 
 typedef struct gbp_ba_graph* gbp_handle;
 
@@ -63,6 +63,15 @@ typedef struct gbp_config {
                                         prologue waits for the tile descriptor, far-ahead L2 prefetch on graphs of more than 8192
                                         tiles; tiles of 32 / 64.  GBP_F_MSG_CAM reads and writes keep the full eta[6] | Lambda[21]
                                         form.  Both builds run the same per-edge arithmetic (gbp_edge.cuh). */
+    /* Landmark CHUNKS (no reference counterpart).  The sum of the factor->keyframe messages of a keyframe is formed per chunk of
+     * consecutive landmarks (tiles never straddle a chunk) and the chunk sums are added in chunk order.  A multi-GPU run gives every
+     * rank whole chunks of the SAME global chunking, so the keyframe beliefs -- and with them the whole trajectory -- are
+     * bit-identical for 1, 2, 4 and 8 GPUs.  Chunk k of lmk_chunks_total covers the global landmarks
+     * [lmk_total * k / lmk_chunks_total, lmk_total * (k + 1) / lmk_chunks_total); this graph holds lmk_chunks of them starting at
+     * chunk lmk_chunk_first, its landmark 0 being global landmark lmk_first.  lmk_chunks = 0: automatic (the whole graph: 8 chunks
+     * from 65536 landmarks on, else 1). */
+    int32_t lmk_chunks, lmk_chunk_first, lmk_chunks_total, reserved0;
+    int64_t lmk_first, lmk_total;
 } gbp_config;
 
 /* Stages of FactorGraph.synchronous_iteration (gbp/gbp.py:86-92), OR-able. */
@@ -94,7 +103,8 @@ typedef enum gbp_field {
                                Factor.factor = (J^T b / var, J^T J / var)  (gbp/gbp.py:287-289)                            */
     GBP_F_ADJ = 12,         /* F x 2 int32 : (camera id, landmark id) = Factor.adj_vIDs (landmark NOT offset by C; read only) */
     GBP_F_FILE_INDEX = 13,  /* F x int32 : position of each factor in the measurement list passed to create (read only)    */
-    GBP_F_CAM_PARTIAL = 14, /* C x 27 : this rank's sum of factor->keyframe messages (multi-GPU exchange buffer; read only) */
+    GBP_F_CAM_PARTIAL = 14, /* chunks x C x 27 : this graph's sums of factor->keyframe messages per landmark chunk (the multi-GPU
+                               exchange buffer; read only) */
     GBP_F_CAM_MU = 15,      /* C x 6 : compact copy of the keyframe means (VariableNode.mu, gbp/gbp.py:193; read only)     */
     GBP_F_LMK_MU = 16,      /* L x 3 : compact copy of the landmark means (read only)                                      */
     GBP_F__COUNT
@@ -136,8 +146,11 @@ int gbp_ba_sizes(gbp_handle h, int64_t out[6]);
  * gbp_plan_sizes: C, L, F, tiles, edges per tile, slots.  gbp_plan_copy: any output may be NULL; tiles = (keyframe, count)
  * pairs; adj = (keyframe, landmark) per factor; lmk_idx per slot (0 in padding slots). */
 typedef struct gbp_plan_s* gbp_plan;
-int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
+/* chunking: NULL = automatic, else {lmk_chunks, lmk_chunk_first, lmk_chunks_total, lmk_first, lmk_total} as in gbp_config */
+int gbp_plan_create(int32_t tile_edges, int32_t lmk_block, const int64_t* chunking, int32_t C, int32_t L, int64_t F, const int32_t* cam_id,
                     const int32_t* lmk_id, gbp_plan* out);
+/* chunk of every tile [tiles]; per keyframe the positions in cam_tiles where its chunks start, C x (chunks + 1); returns the chunk count */
+int gbp_plan_chunks(gbp_plan p, int32_t* tile_chunk, int32_t* cam_chunk_ptr);
 int gbp_plan_sizes(gbp_plan p, int64_t out[6]);
 int gbp_plan_copy(gbp_plan p, int32_t* tiles, int32_t* slot_of_factor, int32_t* file_of_factor, int32_t* adj, int32_t* lmk_idx,
                   int32_t* lmk_ptr, int32_t* lmk_slots, int32_t* cam_tile_ptr, int32_t* cam_tiles);
@@ -145,7 +158,8 @@ void gbp_plan_destroy(gbp_plan p);
 
 /* Engine layout chosen for this graph (no reference counterpart; used by bench.py to count the bytes a sweep moves):
  * out[0] doubles per stored factor->keyframe message (27 full, 18 factored), out[1] L2 prefetch distance in tiles,
- * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice: 1 or 2), out[3] reserved (0). */
+ * out[2] sweep kernel build in use (gbp_config.kernel_variant after the automatic choice: 1 or 2), out[3] landmark chunks of the
+ * keyframe-side sums held by this graph (gbp_config.lmk_chunks after the automatic choice). */
 int gbp_ba_layout(gbp_handle h, int64_t out[4]);
 
 /* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
@@ -167,29 +181,11 @@ int gbp_ba_sweep_local(gbp_handle h, int stages);
 /* The landmark half of update_all_beliefs (gbp/gbp.py:176-198) after a sweep with GBP_STAGE_DEFER_LANDMARKS: needs
  * no communication, so a multi-GPU caller runs it while the keyframe partial sums are being exchanged. */
 int gbp_ba_landmark_update(gbp_handle h);
-/* Finish VariableNode.update_belief (gbp/gbp.py:176-198) for the keyframes: belief = prior + sum over
- * ranks (in rank order) of the partial sums.  `partials` is a DEVICE pointer to nranks x C x 27
- * doubles (e.g. the output of an NCCL all-gather of GBP_F_CAM_PARTIAL); NULL = use this handle's own
- * partial (single GPU). */
-int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks);
+/* Finish VariableNode.update_belief (gbp/gbp.py:176-198) for the keyframes: belief = prior + the chunk sums in chunk order.
+ * `partials` is a DEVICE pointer to n_partials x C x 27 doubles (the output of an all-gather of every rank's
+ * GBP_F_CAM_PARTIAL: ranks in rank order hold the chunks in chunk order); NULL = this handle's own chunk sums (single GPU). */
+int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int n_partials);
 
-/* Peer-memory exchange of the keyframe partial sums (multi-GPU, one process per GPU; no reference counterpart).
- * Opt-in replacement of [all-gather -> gbp_ba_cam_update]: every rank writes its C x 27 partial sums straight into
- * the other ranks' exchange buffers over NVLink (CUDA IPC mappings) and raises a per-CTA flag there; the update
- * kernel of each rank waits for the flags of its own buffer and adds prior + sums in rank order.
- *   gbp_ba_p2p_init    allocates this rank's buffer and returns its CUDA IPC handle (GBP_IPC_HANDLE_BYTES bytes);
- *   gbp_ba_p2p_attach  maps the buffers of all ranks (handles in rank order, own entry ignored);
- *   per iteration:     gbp_ba_sweep_local(h, stages | GBP_STAGE_DEFER_LANDMARKS); gbp_ba_p2p_scatter(h);
- *                      gbp_ba_landmark_update(h);  gbp_ba_p2p_gather_update(h);
- *   gbp_ba_p2p_status  out[0] = exchanges completed, out[1] = waits that timed out (~2 s; a peer is gone).
- * A wait that times out also poisons the keyframe beliefs of its CTA with NaN: a lost exchange never passes as a result.
- * Every rank must destroy its handle only after all ranks stopped iterating (barrier on the host side). */
-#define GBP_IPC_HANDLE_BYTES 64
-int gbp_ba_p2p_init(gbp_handle h, int rank, int nranks, void* ipc_handle_out);
-int gbp_ba_p2p_attach(gbp_handle h, const void* ipc_handles);
-int gbp_ba_p2p_scatter(gbp_handle h);
-int gbp_ba_p2p_gather_update(gbp_handle h);
-int gbp_ba_p2p_status(gbp_handle h, int64_t out[2]);
 /* n x synchronous_iteration(robustify, local_relin) on one GPU (gbp/gbp.py:86-92; the loop of
  * ba.py:84-105 without the client's per-iteration reads): sweep_local + cam_update, replayed from a
  * CUDA graph. */
@@ -233,8 +229,9 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
 
 int gbp_ba_synchronize(gbp_handle h);
 /* Engine tuning knobs (no reference counterpart; measurement scripts): GBP_TUNE_PREFETCH_TILES = L2 prefetch distance of the
- * streaming build in tiles (0 = off; the automatic choice is ~38 k edges ahead). */
-enum { GBP_TUNE_PREFETCH_TILES = 3 };
+ * streaming build in tiles (0 = off; the automatic choice is ~38 k edges ahead); GBP_TUNE_BELIEF_LANES = lanes per landmark in the
+ * belief kernel (1, 8, 32; 0 = chosen by the number of landmarks). */
+enum { GBP_TUNE_PREFETCH_TILES = 3, GBP_TUNE_BELIEF_LANES = 5 };
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value);
 /* Timing helper for benchmarks: runs n_iters iterations bracketed by CUDA events on the handle's
  * stream; *ms_total = elapsed device time, *ms_msg_kernel = summed time of the message kernel alone

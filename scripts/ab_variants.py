@@ -75,16 +75,19 @@ def fr1desk(reps):
             emit({"graph": "fr1desk", "run": tag, "error": f"{type(ex).__name__}: {ex}", "trace": traceback.format_exc()[-600:]})
 
 
-def synthetic(cams, lmks, tiles, blocks, pfs, iters):
+def synthetic(cams, lmks, tiles, blocks, pfs, iters, lanes=(0,)):
     prob = make_synthetic(cams, lmks, 10, seed=0)
     base = None
     for T in tiles:
         for blk in blocks:
+          for ln in lanes:
             for pf in pfs:
-                tag = f"T{T}_blk{blk}_pf{pf}"
+                tag = f"T{T}_blk{blk}_pf{pf}_lanes{ln}"
                 try:
                     g = create_ba_graph(prob, CFG, tile_edges=T, lmk_block=blk)
                     e = g._eng
+                    if ln:
+                        e.tune(L.TUNE_BELIEF_LANES, ln)
                     if pf >= 0:
                         e.tune(L.TUNE_PREFETCH_TILES, pf)
                     g.generate_priors_var(50.0)
@@ -117,12 +120,13 @@ def main():
     ap.add_argument("--blocks", default="0")
     ap.add_argument("--pf", default="-1", help="L2 prefetch distances in tiles (-1 = automatic)")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--lanes", default="0", help="lanes per landmark of the belief kernel (1, 8, 32; 0 = automatic)")
     a = ap.parse_args()
     if a.fr1desk:
         fr1desk(a.reps)
     if a.synthetic:
         synthetic(a.cams, a.lmks, [int(x) for x in a.tiles.split(",")], [int(x) for x in a.blocks.split(",")],
-                  [int(x) for x in a.pf.split(",")], a.iters)
+                  [int(x) for x in a.pf.split(",")], a.iters, [int(x) for x in a.lanes.split(",")])
 
 
 if __name__ == "__main__":

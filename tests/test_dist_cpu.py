@@ -173,19 +173,3 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert np.array_equal(trace[:, 2], r0["trace"][:, 2])
     assert relerr(r0["trace"][:, :2], trace[:, :2]) < 1e-9
     assert relerr(r0["means"], np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])) < 1e-9
-
-
-def test_peer_memory_exchange_needs_the_cuda_engine():
-    """p2p=True is only meaningful with the CUDA engine (CUDA IPC mappings); a stand-in engine must be refused,
-    and a single rank never sets it up."""
-    from gbp_b200.dist import PartitionedBAGraph
-    from gbp_b200.synthetic import make_synthetic
-    prob = make_synthetic(4, 60, 3, seed=2)
-
-    class FakeDist:                     # world > 1 is enough to reach the check; no collective is issued before it
-        pass
-
-    with pytest.raises(ValueError, match="peer-memory exchange"):
-        PartitionedBAGraph(prob, CFG, rank=0, world=2, dist=FakeDist(), engine_factory=lambda s, c: OracleAdapter(s, c), p2p=True)
-    g = PartitionedBAGraph(prob, CFG, rank=0, world=1, engine_factory=lambda s, c: OracleAdapter(s, c), p2p=True)
-    assert g.p2p is False

@@ -13,8 +13,21 @@ def _plan(cam, lmk, C, L, **kw):
     return compile_plan(cam, lmk, C, L, **kw)
 
 
-def _check(plan, cam, lmk, C, L, lblock):
+def _blocks(L, lblock, K):
+    """Landmark -> (block, chunk): every chunk [L k / K, L (k + 1) / K) is cut into blocks of lblock landmarks, numbered chunk by chunk."""
+    blk, chunk, nb = np.zeros(L, np.int64), np.zeros(L, np.int64), 0
+    for k in range(K):
+        l0, l1 = L * k // K, L * (k + 1) // K
+        for b0 in range(l0, l1, lblock):
+            blk[b0:min(l1, b0 + lblock)] = nb
+            nb += 1
+        chunk[l0:l1] = k
+    return blk, chunk
+
+
+def _check(plan, cam, lmk, C, L, lblock, K=1):
     T, tiles, F = plan["T"], plan["tiles"], len(cam)
+    blk_of, chunk_of = _blocks(L, lblock, K)
     order = np.argsort(cam, kind="stable")
     # factor order = the reference's: stable sort of the measurement list by camera
     assert np.array_equal(plan["file_of_factor"], order)
@@ -28,7 +41,7 @@ def _check(plan, cam, lmk, C, L, lblock):
     assert np.array_equal(np.bincount(t_of, minlength=len(tiles)), tiles[:, 1]) and (tiles[:, 1] >= 1).all() and (tiles[:, 1] <= T).all()
     assert np.array_equal(tiles[t_of, 0], fcam)                      # every tile holds edges of ONE keyframe
     # tiles are sorted by (landmark block, keyframe); inside a run the factor order is kept and only the last tile is ragged
-    key = (flmk // lblock).astype(np.int64) * max(C, 1) + fcam
+    key = blk_of[flmk] * max(C, 1) + fcam
     tile_key = np.full(len(tiles), -1, np.int64)
     tile_key[t_of] = key
     assert (np.diff(tile_key) >= 0).all()
@@ -47,6 +60,19 @@ def _check(plan, cam, lmk, C, L, lblock):
     # CSR by keyframe over tiles, tile order inside a keyframe
     assert np.array_equal(np.diff(plan["cam_tile_ptr"]), np.bincount(tiles[:, 0], minlength=C))
     assert np.array_equal(plan["cam_tiles"], np.argsort(tiles[:, 0], kind="stable"))
+    # landmark chunks: a tile lies in ONE chunk; a keyframe's tile list is chunk-major and cam_chunk_ptr marks the chunk starts
+    assert plan["n_chunks"] == K
+    tchunk = np.full(len(tiles), -1, np.int64)
+    tchunk[t_of] = chunk_of[flmk]
+    for t in range(len(tiles)):
+        assert (chunk_of[flmk[t_of == t]] == tchunk[t]).all()
+    assert np.array_equal(plan["tile_chunk"], tchunk)
+    ccp = plan["cam_chunk_ptr"]
+    assert ccp.shape == (C, K + 1)
+    for c in range(C):
+        assert ccp[c, 0] == plan["cam_tile_ptr"][c] and ccp[c, K] == plan["cam_tile_ptr"][c + 1] and (np.diff(ccp[c]) >= 0).all()
+        for k in range(K):
+            assert (tchunk[plan["cam_tiles"][ccp[c, k]:ccp[c, k + 1]]] == k).all()
 
 
 @pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk"])
@@ -56,6 +82,30 @@ def test_plan_of_the_reference_problems(built_library, name, tile, block):
     plan = _plan(P.cam_id, P.lmk_id, P.n_keyframes, P.n_points, tile_edges=tile, lmk_block=block)
     assert plan["T"] == (tile or 32)                                   # small graphs: 32-edge tiles
     _check(plan, np.asarray(P.cam_id), np.asarray(P.lmk_id), P.n_keyframes, P.n_points, block or max(P.n_points, 1))
+
+
+@pytest.mark.parametrize("K,block", [(2, 0), (8, 0), (4, 50), (3, 7)])
+def test_plan_with_landmark_chunks(built_library, K, block):
+    """gbp_config.lmk_chunks: blocks never straddle a chunk, so that a rank holding whole chunks lays out exactly the tiles the
+    single-GPU plan has for those chunks (the basis of bit-identical results on 1, 2, 4 and 8 GPUs)."""
+    P = golden_problem(load_golden("fr1desk"))
+    cam, lmk = np.asarray(P.cam_id), np.asarray(P.lmk_id)
+    plan = _plan(cam, lmk, P.n_keyframes, P.n_points, tile_edges=32, lmk_block=block, chunks=K)
+    _check(plan, cam, lmk, P.n_keyframes, P.n_points, block or max(P.n_points, 1), K)
+    # the sub-problem of chunk range [k0, k1) planned on its own = the corresponding tiles of the whole plan
+    from gbp_b200.dist import local_problem
+    for world in (2,) if K % 2 == 0 else ():
+        for r in range(world):
+            sub, sel, (l0, l1) = local_problem(P, r, world)
+            lp = _plan(sub.cam_id, sub.lmk_id, P.n_keyframes, sub.n_points, tile_edges=32, lmk_block=block or max(P.n_points, 1),
+                       chunks=(K // world, r * K // world, K, l0, P.n_points))
+            mine = np.nonzero((plan["tile_chunk"] >= r * K // world) & (plan["tile_chunk"] < (r + 1) * K // world))[0]
+            assert np.array_equal(lp["tiles"], plan["tiles"][mine])
+            whole = plan["lmk_idx"].reshape(-1, 32)[mine]
+            local = lp["lmk_idx"].reshape(-1, 32)
+            valid = np.arange(32)[None, :] < lp["tiles"][:, 1:2]
+            assert np.array_equal((local + l0)[valid], whole[valid])            # the same edges in the same slots
+            assert np.array_equal(lp["tile_chunk"] + r * K // world, plan["tile_chunk"][mine])
 
 
 def test_plan_shuffled_file_order_and_isolated_variables(built_library):
@@ -71,14 +121,14 @@ def test_plan_shuffled_file_order_and_isolated_variables(built_library):
 
 
 def test_plan_large_graph_auto_tiling(built_library):
-    """Automatic choices: 64-edge tiles from 56832 factors on; landmark blocks of 262144 once the belief rows exceed
-    24 MB (the synthetic 1 M-landmark graph is cut into 4 blocks)."""
+    """Automatic choices: 64-edge tiles from 56832 factors on; 8 landmark chunks from 65536 landmarks on (the keyframe-side sums
+    are associated chunk by chunk, identically on 1, 2, 4 and 8 GPUs); landmark blocks of at most 262144 inside a chunk."""
     from gbp_b200.synthetic import make_synthetic
     prob = make_synthetic(50, 300_000, 4, seed=2)
     plan = _plan(prob.cam_id, prob.lmk_id, prob.n_keyframes, prob.n_points)
     assert plan["T"] == 64
-    _check(plan, np.asarray(prob.cam_id), np.asarray(prob.lmk_id), prob.n_keyframes, prob.n_points, 262144)
-    assert len(np.unique(np.asarray(prob.lmk_id) // 262144)) == 2
+    _check(plan, np.asarray(prob.cam_id), np.asarray(prob.lmk_id), prob.n_keyframes, prob.n_points, 262144, K=8)
+    assert plan["n_chunks"] == 8 and len(np.unique(plan["tile_chunk"])) == 8
     waste = plan["n_slots"] / len(prob.cam_id) - 1.0
     assert waste < 0.05                                                 # padding slots: < 5 % on this graph
 
