@@ -230,6 +230,8 @@ class Ctx:
             import threading
             threading.Timer(30.0, lambda: os._exit(0)).start()
             self.torch.cuda.synchronize()
+            from gbp_b200.dist import shutdown
+            shutdown()                      # the library's own NCCL communicator
             self.dist.destroy_process_group()
             os._exit(0)
 
@@ -508,38 +510,39 @@ def bench_synthetic_1gpu(ctx, args):
     return synth, roof
 
 
+def L_nccl_version():
+    from gbp_b200 import _lib as L
+    return L.comm_version()
+
+
 def phase_breakdown(ctx, pg, n=30):
-    """Where an iteration of the partitioned graph spends its time on this rank: the same calls as
-    PartitionedBAGraph.synchronous_iteration, issued eagerly with CUDA events between the phases (medians over n iterations,
-    max over ranks).  Eager launches have gaps the captured graph does not, so the sum is an upper bound of the captured iteration."""
+    """Where an iteration of the partitioned graph spends its time on this rank: the three phases issued one after the other on
+    the engine's stream with CUDA events between them (medians over n iterations, max over ranks).  In the real iteration (one
+    CUDA-graph replay) the exchange runs on a high-priority side stream WHILE the landmark beliefs are updated, so the captured
+    iteration is shorter than the sum of the phases."""
     from gbp_b200 import _lib as L
     torch = ctx.torch
-    a = pg.adapter
+    eng = pg.engine
     st = L.ST_MESSAGES | L.ST_BELIEFS | L.ST_DEFER_LANDMARKS | L.ST_ROBUSTIFY | L.ST_RELIN | L.ST_LOCAL_DAMPING
     rows = []
     for it in range(n + 5):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        with pg._stream_ctx():
-            ev[0].record()
-            a.sweep_local(st)                       # sweep_kernel + keyframe partial sums (belief_kernel, keyframe part)
-            ev[1].record()
-            work = pg.dist.all_gather_into_tensor(pg._gather, a.partial_tensor(), async_op=True)
-            ev[2].record()
-            a.landmark_update()
-            ev[3].record()
-            work.wait()
-            a.apply_gathered(pg._gather, pg.world)
-            ev[4].record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        eng.sweep_local(st)                         # sweep_kernel + keyframe chunk sums (belief_kernel, keyframe CTAs)
+        ev[1].record()
+        eng.exchange()                              # ncclAllGather of the chunk sums + cam_update_kernel
+        ev[2].record()
+        eng.landmark_update()                       # belief_kernel, landmark CTAs
+        ev[3].record()
         torch.cuda.synchronize()
         pg.n_iterations += 1
         if it >= 5:
-            rows.append([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(4)] + [ev[0].elapsed_time(ev[4]) * 1e3])
+            rows.append([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(3)] + [ev[0].elapsed_time(ev[3]) * 1e3])
     med = np.median(np.array(rows), axis=0)
     med = [ctx.max_over_ranks(float(x)) for x in med]
-    names = ["local_sweep_and_keyframe_partial_sums", "exchange_issue", "landmark_belief_update",
-             "exchange_wait_and_keyframe_update", "total_eager"]
+    names = ["local_sweep_and_keyframe_chunk_sums", "exchange_and_keyframe_update", "landmark_belief_update", "total_serialised"]
     out = dict(zip(names, med))
-    out["note"] = "eager launches with CUDA events between the phases, median of %d iterations, max over ranks; the timed solve replays a captured graph without the launch gaps" % n
+    out["note"] = "phases serialised on one stream with CUDA events between them, median of %d iterations, max over ranks; the timed solve replays one CUDA graph per iteration in which the exchange (side stream) overlaps the landmark update" % n
     return out
 
 
@@ -567,8 +570,7 @@ def bench_partitioned(ctx, args):
         g.update_all_beliefs()
 
     def solve(g):
-        for _ in range(S):
-            g.synchronous_iteration(robustify=True, local_relin=True)
+        g.iterate(S, robustify=True, local_relin=True)
 
     t0 = time.perf_counter()
     pg = build()
@@ -667,7 +669,7 @@ def bench_partitioned(ctx, args):
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic BAL graph (gbp_b200/synthetic.py, seed 0): keyframes on a circle, landmarks in a cube, 10 observations per landmark, 2 px noise",
             "config": bench_config(world, args.synth_cams, args.synth_lmks),
-            "engine": {"exchange": "NCCL all-gather of the keyframe partial sums", "iteration_captured_in_cuda_graph": bool(captured), "layout": layout},
+            "engine": {"exchange": "ncclAllGather of the keyframe chunk sums, called by libgbp_b200 (gbp_ba_attach_comm) on a high-priority side stream; overlaps the landmark belief update", "nccl_version": L_nccl_version(), "iteration_captured_in_cuda_graph": bool(captured), "layout": layout},
             "ms_per_iteration": 1e3 * t_dev / (args.steps * S), "clocks": clocks,
             "algorithmic_bytes_per_iteration": total_b_layout,
             "frac_of_hbm_peak_whole_iteration_per_gpu": total_b_layout / world / (t_dev / (args.steps * S)) / 1e9 / ctx.hbm_peak,

@@ -12,7 +12,8 @@ import numpy as np
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+COMM_ID_BYTES = 128
 
 # gbp_field
 (F_CAM_BELIEF, F_LMK_BELIEF, F_CAM_PRIOR, F_LMK_PRIOR, F_MSG_CAM, F_MSG_LMK, F_LINPOINT, F_ITERS,
@@ -22,7 +23,7 @@ ABI_VERSION = 2
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
-TUNE_PREFETCH_TILES, TUNE_BELIEF_LANES = 3, 5
+TUNE_PREFETCH_TILES, TUNE_BELIEF_LANES, TUNE_LMK_STORE_POLICY = 3, 5, 6
 
 # field -> (index kind, dtype, row width)
 FIELD_SHAPES = {
@@ -61,6 +62,7 @@ EXPORTS = [
     "gbp_cache_configure", "gbp_cache_stats", "gbp_ba_tune",
     "gbp_lin_create", "gbp_lin_destroy", "gbp_lin_set_messages", "gbp_lin_update_beliefs", "gbp_lin_iterate", "gbp_lin_energy", "gbp_lin_read",
     "gbp_lin_joint_solve", "gbp_lin_launch_count",
+    "gbp_comm_unique_id", "gbp_comm_version", "gbp_comm_create", "gbp_comm_destroy", "gbp_ba_attach_comm", "gbp_ba_detach_comm", "gbp_ba_comm_info", "gbp_ba_exchange",
 ]
 
 _lib = None
@@ -139,10 +141,41 @@ def load():
     lib.gbp_lin_joint_solve.argtypes = [vp, vp, vp, vp, vp]
     lib.gbp_lin_launch_count.argtypes = [vp]
     lib.gbp_lin_launch_count.restype = C.c_int64
+    lib.gbp_comm_unique_id.argtypes = [vp]
+    lib.gbp_comm_version.restype = C.c_int
+    lib.gbp_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.gbp_comm_destroy.argtypes = [vp]
+    lib.gbp_ba_attach_comm.argtypes = [vp, vp]
+    lib.gbp_ba_detach_comm.argtypes = [vp]
+    lib.gbp_ba_comm_info.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.gbp_ba_exchange.argtypes = [vp]
     if lib.gbp_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libgbp_b200 ABI {lib.gbp_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
+
+
+def prefer_bundled_nccl():
+    """Point the library's dlopen at the NCCL that PyTorch bundles (nvidia/nccl/lib/libnccl.so.2) when there is one: a process
+    cannot hold two different libnccl.so.2, and torch needs its own.  No-op when $GBP_NCCL_LIB is set or there is no bundled copy."""
+    if os.environ.get("GBP_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["GBP_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+def comm_version():
+    """NCCL version code the library would use (0: no libnccl)."""
+    prefer_bundled_nccl()
+    return int(load().gbp_comm_version())
 
 
 def check(status):

@@ -10,6 +10,8 @@ arrays for graphs too large for text.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -54,6 +56,10 @@ def read_bal(path) -> BALProblem:
         return BALProblem(d["cam_id"], d["lmk_id"], d["z"], d["cam_means"], d["lmk_means"], d["K4"])
     import ctypes as C
     from . import _lib as L
+    if not os.path.exists(L.LIB_PATH):
+        # reading a problem file is host-only work: a machine without the CUDA build (no nvcc) can still load and inspect
+        # problems with the Python reader (same acceptance rules, ~8x slower); everything that computes still needs the library
+        return read_bal_python(path)
     lib = L.load()
     h = C.c_void_p()
     L.check(lib.gbp_bal_open(str(path).encode(), C.byref(h)))

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libgbp_b200.so")
 SOURCES = ["gbp_ba.cu"]
-HEADERS = ["gbp_math.cuh", "gbp_edge.cuh", "gbp_kernels.cuh", "gbp_bal.cpp.inc", "gbp_lin.cu.inc", os.path.join("..", "..", "include", "gbp_b200.h")]
+HEADERS = ["gbp_math.cuh", "gbp_edge.cuh", "gbp_kernels.cuh", "gbp_bal.cpp.inc", "gbp_lin.cu.inc", "gbp_dist.cu.inc", os.path.join("..", "..", "include", "gbp_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -99,6 +99,7 @@ struct gbp_ba_graph {
     long long launches = 0;
     int K_chunks = 1;         // landmark chunks of the keyframe-side sums (gbp_config)
     int belief_lanes = 0;     // lanes per landmark in belief_kernel: 0 = by graph size (GBP_TUNE_BELIEF_LANES)
+    int lmk_policy = 0;       // L2 policy of the factor->landmark message stores (GBP_TUNE_LMK_STORE_POLICY)
 
     // host copies (factor order)
     std::vector<int> h_slot_of_factor, h_file_of_factor, h_adj;
@@ -121,6 +122,13 @@ struct gbp_ba_graph {
     std::map<int, cudaGraphExec_t> snap_graphs;
     void* snap_ptr = nullptr;
     size_t snap_bytes = 0;   // metric_out .. end of lmk_belief (start of the arena)
+
+    // multi-GPU (gbp_ba_attach_comm): this graph is one rank's share of a landmark-partitioned graph
+    void* comm = nullptr;            // gbp_comm_s* (not owned)
+    int rank = 0, nranks = 1;
+    double* gather = nullptr;        // [nranks x K_chunks][C][27] chunk sums of every rank, rank order = chunk order (own cudaMalloc)
+    cudaStream_t side = nullptr;     // high-priority stream of the keyframe branch (chunk sums -> all-gather -> keyframe beliefs)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ~gbp_ba_graph();
 };
@@ -212,8 +220,12 @@ void cache_put(Shell&& sh) {
 
 }  // namespace
 
+static void comm_teardown(gbp_ba_graph* g);   // gbp_dist.cu.inc
+
 gbp_ba_graph::~gbp_ba_graph() {
     if (snap_event) cudaEventDestroy(snap_event);
+    const bool had_comm = comm != nullptr;
+    if (had_comm) comm_teardown(this);   // drops the CUDA graphs (they hold collective nodes of this communicator) first
     // everything else goes back to the shell cache (the stream was synchronised by gbp_ba_destroy; a graph that dies
     // on an error path of gbp_ba_create has nothing in flight that reads the arena after its failed call returned)
     Shell sh;
@@ -222,7 +234,7 @@ gbp_ba_graph::~gbp_ba_graph() {
     sh.stage = stage; sh.stage_bytes = stage_bytes;
     sh.graphs = std::move(graphs); sh.snap_graphs = std::move(snap_graphs); sh.snap_ptr = snap_ptr;
     sh.key = make_key(this);
-    sh.has_key = arena.base != nullptr;
+    sh.has_key = arena.base != nullptr && !had_comm;
     if (arena.base || stage) {
         if (stream) cudaStreamSynchronize(stream);
         cache_put(std::move(sh));
@@ -258,7 +270,7 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std;
     p.eta_damping = g->cfg.eta_damping; p.beta = g->cfg.beta; p.nstds = g->cfg.Nstds;
     p.num_undamped = g->cfg.num_undamped_iters; p.min_linear = g->cfg.min_linear_iters;
-    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles; p.pf_dist = g->pf_dist;
+    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles; p.pf_dist = g->pf_dist; p.lmk_policy = g->lmk_policy;
     return p;
 }
 
@@ -294,7 +306,8 @@ int launch_sweep(gbp_ba_graph* g, int stages) {
 }
 
 // landmark beliefs + keyframe partial sums (+ keyframe beliefs when finalise); parts: bit0 keyframes, bit1 landmarks
-int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
+int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, cudaStream_t stream = nullptr) {
+    if (!stream) stream = g->stream;
     BeliefParams p{};
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
@@ -309,9 +322,9 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3) {
     const int blocks = ((parts & 2) ? (g->L + per_cta - 1) / per_cta : 0) + ((parts & 1) ? (g->C + 3) / 4 : 0);
     if (blocks == 0) return GBP_OK;
     switch (lanes) {
-        case 1: belief_kernel<1><<<blocks, 128, 0, g->stream>>>(p); break;
-        case 8: belief_kernel<8><<<blocks, 128, 0, g->stream>>>(p); break;
-        default: belief_kernel<32><<<blocks, 128, 0, g->stream>>>(p); break;
+        case 1: belief_kernel<1><<<blocks, 128, 0, stream>>>(p); break;
+        case 8: belief_kernel<8><<<blocks, 128, 0, stream>>>(p); break;
+        default: belief_kernel<32><<<blocks, 128, 0, stream>>>(p); break;
     }
     g->launches++;
     CU(cudaGetLastError());
@@ -399,6 +412,16 @@ void* field_dev_ptr(gbp_ba_graph* g, int field) {
     }
 }
 
+int comm_all_reduce(gbp_ba_graph* g, double* dev, size_t n, bool max_op);   // gbp_dist.cu.inc: in place over the ranks, on the handle's stream
+int enqueue_beliefs(gbp_ba_graph* g);   // gbp_dist.cu.inc: belief update after a sweep, with the keyframe exchange when a communicator is attached
+
+// one synchronous iteration on the handle's stream(s): sweep, then the belief update
+int enqueue_iteration(gbp_ba_graph* g, int stages) {
+    int rc = launch_sweep(g, stages);
+    if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = enqueue_beliefs(g);
+    return rc;
+}
+
 // CUDA graph of `reps` consecutive iterations [sweep, beliefs] x reps (fewer, longer launches: the gap between two
 // graph launches is larger than the gap between two nodes of one graph, which matters at 10 us per iteration)
 int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
@@ -409,10 +432,7 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     CU(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
     const long long before = g->launches;
     int rc = GBP_OK;
-    for (int r = 0; r < reps && rc == GBP_OK; ++r) {
-        rc = launch_sweep(g, stages);
-        if (rc == GBP_OK && (stages & ST_BELIEFS)) rc = launch_belief(g, 1, 3);
-    }
+    for (int r = 0; r < reps && rc == GBP_OK; ++r) rc = enqueue_iteration(g, stages);
     g->launches = before;  // capture does not execute
     cudaError_t e = cudaStreamEndCapture(g->stream, &graph);
     if (rc != GBP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -425,6 +445,10 @@ int get_graph(gbp_ba_graph* g, int stages, cudaGraphExec_t* out, int reps = 1) {
     *out = exec;
     return GBP_OK;
 }
+
+// kernels of this library per synchronous iteration: sweep + beliefs, or with a communicator sweep, landmark beliefs, keyframe
+// chunk sums, keyframe beliefs (the collective's own kernel is not counted)
+int launches_per_iteration(const gbp_ba_graph* g) { return (g->n_tiles > 0 ? 1 : 0) + (g->comm ? 3 : 1); }
 
 int iteration_stages(int robustify, int local_relin) {
     // synchronous_iteration (gbp/gbp.py:86-92) for a graph with nonlinear factors
@@ -865,6 +889,10 @@ int gbp_ba_prior_scan(gbp_handle h, double* cam_max) {
     if (h->C > 0) {
         cam_max_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->tile_max.p, h->cam_tile_ptr.p, h->cam_tiles.p, h->C, h->cam_max.p);
         CU(cudaGetLastError());
+        if (h->comm) {   // the maximum over the factors of a keyframe on EVERY rank (gbp/gbp_ba.py:25-30 over the whole graph)
+            int rc = comm_all_reduce(h, h->cam_max.p, (size_t)h->C, /*max*/ true);
+            if (rc != GBP_OK) return rc;
+        }
         if (cam_max) CU(cudaMemcpyAsync(cam_max, h->cam_max.p, (size_t)h->C * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
@@ -949,7 +977,7 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
     constexpr int REPS = 8;
-    const int per_iter = (h->n_tiles > 0 ? 1 : 0) + 1;
+    const int per_iter = launches_per_iteration(h);
     int left = n_iters;
     if (left >= REPS && h->n_tiles <= 8192) {   // small graphs only: there the launch gaps are a visible share of an iteration
         cudaGraphExec_t exec8;
@@ -971,22 +999,7 @@ int gbp_ba_update_beliefs(gbp_handle h) {
     CHECK_H(h);
     int rc = launch_sweep(h, ST_BELIEFS);  // only the per-tile sums of the stored messages
     if (rc != GBP_OK) return rc;
-    return launch_belief(h, 1);
-}
-
-int gbp_ba_metrics(gbp_handle h, double out[3]) {
-    CHECK_H(h);
-    if (!out) return fail(GBP_ERR_INVALID, "null out");
-    out[0] = out[1] = out[2] = 0.0;
-    if (h->n_tiles == 0) return GBP_OK;
-    int rc = DISPATCH_T(h, launch_metric_t);
-    if (rc != GBP_OK) return rc;
-    reduce_rows_kernel<3><<<1, 256, 0, h->stream>>>(h->tile_metric.p, h->n_tiles, h->metric_out.p);
-    h->launches += 2;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, h->metric_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return GBP_OK;
+    return enqueue_beliefs(h);
 }
 
 namespace {
@@ -1000,9 +1013,23 @@ int enqueue_metrics(gbp_ba_graph* h) {
     } else {
         CU(cudaMemsetAsync(h->metric_out.p, 0, 3 * sizeof(double), h->stream));
     }
+    if (h->comm) return comm_all_reduce(h, h->metric_out.p, 3, /*max*/ false);
     return GBP_OK;
 }
 }  // namespace
+
+int gbp_ba_metrics(gbp_handle h, double out[3]) {
+    CHECK_H(h);
+    if (!out) return fail(GBP_ERR_INVALID, "null out");
+    out[0] = out[1] = out[2] = 0.0;
+    if (h->n_tiles == 0 && !h->comm) return GBP_OK;
+    int rc = enqueue_metrics(h);   // with a communicator: summed over the ranks (a rank without edges still joins the sum)
+    if (rc != GBP_OK) return rc;
+    CU(cudaMemcpyAsync(out, h->metric_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GBP_OK;
+}
+
 
 int gbp_ba_snapshot_layout(gbp_handle h, uint64_t out[4]) {
     if (!h || !out) return fail(GBP_ERR_INVALID, "null argument");
@@ -1043,8 +1070,7 @@ int gbp_ba_iterate_snapshot(gbp_handle h, int robustify, int local_relin, void* 
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         const long long before = h->launches;
-        int rc = launch_sweep(h, st);
-        if (rc == GBP_OK) rc = launch_belief(h, 1);
+        int rc = enqueue_iteration(h, st);
         if (rc == GBP_OK) rc = enqueue_metrics(h);
         cudaError_t e = cudaSuccess;
         if (rc == GBP_OK) e = cudaMemcpyAsync(region, h->arena.base, h->snap_bytes, cudaMemcpyDeviceToHost, h->stream);
@@ -1061,7 +1087,7 @@ int gbp_ba_iterate_snapshot(gbp_handle h, int robustify, int local_relin, void* 
         h->snap_graphs[st] = exec;
     }
     CU(cudaGraphLaunch(exec, h->stream));
-    h->launches += (h->n_tiles > 0 ? 4 : 1);
+    h->launches += launches_per_iteration(h) + (h->n_tiles > 0 ? 2 : 0);
     CU(cudaEventRecord(h->snap_event, h->stream));
     return GBP_OK;
 }
@@ -1135,8 +1161,8 @@ int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes) {
     if (!host_src) return fail(GBP_ERR_INVALID, "null source");
     if (fi.indexed != 2) {
         CU(cudaMemcpyAsync(field_dev_ptr(h, field), host_src, need, cudaMemcpyHostToDevice, h->stream));
-        if (field == GBP_F_CAM_BELIEF) extract_mu_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_belief.p, h->C, 6, CAM_B, h->cam_mu.p);
-        if (field == GBP_F_LMK_BELIEF) extract_mu_kernel<<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->lmk_belief.p, h->L, 3, LMK_B, h->lmk_mu.p);
+        if (field == GBP_F_CAM_BELIEF) refresh_mu_kernel<6><<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_belief.p, h->C, CAM_B, h->cam_mu.p);
+        if (field == GBP_F_LMK_BELIEF) refresh_mu_kernel<3><<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->lmk_belief.p, h->L, LMK_B, h->lmk_mu.p);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
         if (field == GBP_F_CAM_PRIOR || field == GBP_F_LMK_PRIOR) h->priors_set = true;
@@ -1211,6 +1237,15 @@ int gbp_ba_tune(gbp_handle h, int knob, int64_t value) {
             for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
             h->snap_graphs.clear();
             return GBP_OK;
+        case GBP_TUNE_LMK_STORE_POLICY:
+            if (value < 0 || value > 2) return fail(GBP_ERR_INVALID, "store policy: 0 (default), 1 (evict_last) or 2 (evict_first)");
+            CU(cudaStreamSynchronize(h->stream));
+            h->lmk_policy = (int)value;
+            for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+            h->graphs.clear();
+            for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
+            h->snap_graphs.clear();
+            return GBP_OK;
         case GBP_TUNE_PREFETCH_TILES:
             if (value < 0) return fail(GBP_ERR_INVALID, "prefetch distance must be >= 0");
             CU(cudaStreamSynchronize(h->stream));
@@ -1247,7 +1282,7 @@ int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_r
         for (int i = 0; i < n_iters; ++i) CU(cudaGraphLaunch(exec, h->stream));
         CU(cudaEventRecord(ev.e1, h->stream));
         CU(cudaEventSynchronize(ev.e1));
-        h->launches += 2LL * n_iters;
+        h->launches += (long long)launches_per_iteration(h) * n_iters;
         if (ms_total) CU(cudaEventElapsedTime(ms_total, ev.e0, ev.e1));
         return GBP_OK;
     }
@@ -1269,7 +1304,7 @@ int gbp_ba_time_iterations(gbp_handle h, int n_iters, int robustify, int local_r
         int rc = launch_sweep(h, st);
         if (rc != GBP_OK) return rc;
         CU(cudaEventRecord(ev[2 * i + 1], h->stream));
-        rc = launch_belief(h, 1);
+        rc = enqueue_beliefs(h);
         if (rc != GBP_OK) return rc;
     }
     CU(cudaEventRecord(ev[2 * n_iters + 1], h->stream));
@@ -1374,5 +1409,6 @@ void gbp_plan_destroy(gbp_plan p) { delete p; }
 
 }  // extern "C"
 
+#include "gbp_dist.cu.inc"
 #include "gbp_bal.cpp.inc"
 #include "gbp_lin.cu.inc"

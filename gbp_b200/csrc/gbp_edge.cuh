@@ -41,6 +41,7 @@ struct SweepParams {
     int num_undamped, min_linear, loss, stages;
     int n_tiles;
     int pf_dist;   // > 0: a CTA also prefetches the streams of tile (its tile + pf_dist) into L2 (early-issue kernels)
+    int lmk_policy;   // L2 policy of the factor->landmark message stores (re-read by belief_kernel): 0 default, 1 evict_last, 2 evict_first
 };
 
 // per-edge register inputs fetched straight from global memory

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
         const uint64_t pol = policy_evict_first();
         if (p.stages & ST_MESSAGES) {
             bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
-            bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+            if (p.lmk_policy == 0) bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
+            else bulk_s2g_hint(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8, p.lmk_policy == 1 ? policy_evict_last() : pol);
         }
         if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
         bulk_commit();
@@ -658,11 +659,27 @@ __global__ void init_belief_kernel(const double* mu0, int V, int N, int brow, do
     }
 }
 
-// compact means <- mean part of the belief rows (after the client wrote a belief table)
-__global__ void extract_mu_kernel(const double* belief, int V, int N, int brow, double* mu_compact) {
+// after the client wrote a belief table: the mean of a variable with a positive-definite precision is Lambda^-1 eta, as every
+// consumer of the reference computes it (gbp/gbp.py:71, 192-193) -- a written `mu` only stands where Lambda is still zero (the
+// initial state); then the compact means are refreshed
+template <int N>
+__global__ void refresh_mu_kernel(double* belief, int V, int brow, double* mu_compact) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    for (int k = 0; k < N; ++k) mu_compact[(long long)v * N + k] = belief[(long long)v * brow + brow - N + k];
+    double* row = belief + (long long)v * brow;
+    bool pd = true;
+    for (int i = 0; i < N; ++i) pd = pd && row[N + sidx<N>(i, i)] > 0.0;
+    if (pd) {
+        double lam[N * (N + 1) / 2], eta[N], mu[N];
+        for (int k = 0; k < N * (N + 1) / 2; ++k) lam[k] = row[N + k];
+        for (int k = 0; k < N; ++k) eta[k] = row[k];
+        spd_solve<N>(lam, eta, mu);
+        bool ok = true;
+        for (int k = 0; k < N; ++k) ok = ok && (mu[k] == mu[k]);      // not positive definite after all: keep the written mean
+        if (ok)
+            for (int k = 0; k < N; ++k) row[brow - N + k] = mu[k];
+    }
+    for (int k = 0; k < N; ++k) mu_compact[(long long)v * N + k] = row[brow - N + k];
 }
 
 // dst[f][w] = src[slot_of_factor[f]][w]  (rows of W 4-byte words)

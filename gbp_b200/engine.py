@@ -31,6 +31,33 @@ def pack_sym(full):
     return np.ascontiguousarray(full[..., iu[0], iu[1]])
 
 
+class Communicator:
+    """One NCCL communicator of this process (one GPU), created by the library (`gbp_comm_create`).  One per process and
+    device is enough: it outlives the graphs that attach to it (creating one costs seconds)."""
+
+    def __init__(self, unique_id, rank, nranks, device=0):
+        if len(unique_id) != L.COMM_ID_BYTES:
+            raise ValueError("unique_id must be the %d bytes of Communicator.unique_id()" % L.COMM_ID_BYTES)
+        L.prefer_bundled_nccl()
+        self._lib = L.load()
+        self.handle = C.c_void_p()
+        self.rank, self.nranks, self.device = int(rank), int(nranks), int(device)
+        L.check(self._lib.gbp_comm_create(C.c_char_p(unique_id), int(rank), int(nranks), int(device), C.byref(self.handle)))
+
+    @staticmethod
+    def unique_id():
+        """A fresh NCCL unique id (bytes); one rank makes it, every rank passes it to the constructor."""
+        L.prefer_bundled_nccl()
+        buf = C.create_string_buffer(L.COMM_ID_BYTES)
+        L.check(L.load().gbp_comm_unique_id(buf))
+        return buf.raw
+
+    def destroy(self):
+        if self.handle:
+            L.check(self._lib.gbp_comm_destroy(self.handle))
+            self.handle = C.c_void_p()
+
+
 class BAEngine:
     def __init__(self, cam_id, lmk_id, z, cam_mu0, lmk_mu0, K4, configs, device=0, stream=None,
                  tile_edges=0, lmk_block=0, kernel_variant=0, chunks=None):
@@ -39,6 +66,7 @@ class BAEngine:
         lib = L.load()
         self._lib = lib
         self._h = None
+        self._comm = None
         cam_id = np.ascontiguousarray(cam_id, dtype=np.int32)
         lmk_id = np.ascontiguousarray(lmk_id, dtype=np.int32)
         z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
@@ -120,6 +148,26 @@ class BAEngine:
     def cam_update(self, partials_dev_ptr=None, nranks=1):
         L.check(self._lib.gbp_ba_cam_update(self._h, C.c_void_p(partials_dev_ptr) if partials_dev_ptr else None,
                                             int(nranks)))
+
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU, NCCL called by the library)
+    def attach_comm(self, comm):
+        """Collective over the ranks of `comm` (a Communicator).  From now on iterate / update_beliefs exchange the keyframe chunk
+        sums, generate_priors (without cam_max) and prior_scan take the keyframe maxima over all ranks and metrics() sums over the
+        whole graph.  Detach or close this engine before the communicator is destroyed."""
+        L.check(self._lib.gbp_ba_attach_comm(self._h, comm.handle))
+        self._comm = comm          # keeps it alive
+
+    def detach_comm(self):
+        L.check(self._lib.gbp_ba_detach_comm(self._h))
+        self._comm = None
+
+    def comm_info(self):
+        out = (C.c_int32 * 2)()
+        L.check(self._lib.gbp_ba_comm_info(self._h, out))
+        return int(out[0]), int(out[1])
+
+    def exchange(self):
+        L.check(self._lib.gbp_ba_exchange(self._h))
 
     def iterate(self, n_iters=1, robustify=False, local_relin=True):
         L.check(self._lib.gbp_ba_iterate(self._h, int(n_iters), int(bool(robustify)), int(bool(local_relin))))

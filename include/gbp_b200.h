@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GBP_B200_ABI_VERSION 2
+#define GBP_B200_ABI_VERSION 3
 
 typedef struct gbp_ba_graph* gbp_handle;
 
@@ -38,7 +38,8 @@ typedef enum gbp_status {
     GBP_ERR_INVALID = 1,   /* bad argument / inconsistent graph                      */
     GBP_ERR_CUDA = 2,      /* CUDA runtime error (message in gbp_last_error)         */
     GBP_ERR_NO_DEVICE = 3, /* no CUDA device: there is NO CPU fallback               */
-    GBP_ERR_STATE = 4      /* call order violated (e.g. sweep before priors)         */
+    GBP_ERR_STATE = 4,     /* call order violated (e.g. sweep before priors)         */
+    GBP_ERR_COMM = 5       /* NCCL missing or a collective failed                    */
 } gbp_status;
 
 typedef enum gbp_loss { GBP_LOSS_NONE = 0, GBP_LOSS_HUBER = 1, GBP_LOSS_CONSTANT = 2 } gbp_loss;
@@ -162,9 +163,9 @@ void gbp_plan_destroy(gbp_plan p);
  * keyframe-side sums held by this graph (gbp_config.lmk_chunks after the automatic choice). */
 int gbp_ba_layout(gbp_handle h, int64_t out[4]);
 
-/* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  With nranks > 1 the per-camera maxima
- * must be combined across ranks: call gbp_ba_prior_scan first, max-reduce the C doubles it returns
- * over ranks, and pass them to gbp_ba_generate_priors as cam_max (NULL = use the local scan). */
+/* BAFactorGraph.generate_priors_var (gbp/gbp_ba.py:20-34).  The per-keyframe maxima must cover the factors of ALL ranks: with a
+ * communicator attached gbp_ba_prior_scan reduces them itself; a client with its own transport calls gbp_ba_prior_scan,
+ * max-reduces the C doubles it returns over the ranks and passes them to gbp_ba_generate_priors as cam_max (NULL = scan here). */
 int gbp_ba_prior_scan(gbp_handle h, double* cam_max /* C, host */);
 int gbp_ba_generate_priors(gbp_handle h, double weaker_factor, const double* cam_max /* C or NULL */);
 /* BAFactorGraph.set_priors_var (gbp/gbp_ba.py:44-52): prior Lambda = given packed precision,
@@ -186,11 +187,38 @@ int gbp_ba_landmark_update(gbp_handle h);
  * GBP_F_CAM_PARTIAL: ranks in rank order hold the chunks in chunk order); NULL = this handle's own chunk sums (single GPU). */
 int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int n_partials);
 
-/* n x synchronous_iteration(robustify, local_relin) on one GPU (gbp/gbp.py:86-92; the loop of
- * ba.py:84-105 without the client's per-iteration reads): sweep_local + cam_update, replayed from a
- * CUDA graph. */
+/* ---- multi-GPU: one process per GPU, NCCL (no reference counterpart: the reference is one Python process) ----------------
+ * The graph is partitioned by LANDMARK: every rank creates its handle from all keyframes, a contiguous landmark range
+ * and the measurements of those landmarks, with gbp_config.lmk_chunks / lmk_chunk_first / lmk_chunks_total / lmk_first /
+ * lmk_total naming its share of ONE global landmark chunking (lmk_chunks_total / nranks chunks per rank).  Landmarks are
+ * interior to a rank; the keyframes are the boundary and are replicated.  gbp_comm_unique_id (one rank) -> the id reaches the
+ * other ranks by the client's own means -> gbp_comm_create on every rank (collective; one communicator per process, it outlives
+ * the graphs: creating one costs seconds) -> gbp_ba_attach_comm for every graph (collective).  From then on
+ *   gbp_ba_iterate / gbp_ba_update_beliefs / gbp_ba_iterate_snapshot  exchange the keyframe chunk sums with ONE ncclAllGather
+ *       per iteration on a high-priority side stream while the landmark beliefs are updated on the handle's stream, and every
+ *       rank adds the chunk sums in chunk order: keyframe beliefs are bit-identical on every rank AND to the single-GPU run
+ *       with the same chunking; an iteration stays one CUDA-graph replay per rank;
+ *   gbp_ba_prior_scan / gbp_ba_generate_priors(cam_max = NULL)  take the per-keyframe maximum over all ranks (ncclAllReduce max);
+ *   gbp_ba_metrics / snapshots  return sums over the WHOLE graph (ncclAllReduce sum of the three numbers).
+ * Every rank must make the same sequence of these calls.  libnccl.so.2 is loaded with dlopen on first use (GBP_ERR_COMM when
+ * it is missing); a single-GPU client never needs it. */
+#define GBP_COMM_ID_BYTES 128
+int gbp_comm_unique_id(void* id /* GBP_COMM_ID_BYTES, out */);
+int gbp_comm_version(void);                                   /* NCCL version code, 0 when libnccl cannot be loaded */
+typedef struct gbp_comm_s* gbp_comm;
+int gbp_comm_create(const void* id /* GBP_COMM_ID_BYTES */, int rank, int nranks, int device, gbp_comm* out);
+int gbp_comm_destroy(gbp_comm c);                             /* GBP_ERR_STATE while graphs are attached */
+int gbp_ba_attach_comm(gbp_handle h, gbp_comm c);             /* the graph must be detached or destroyed before the communicator */
+int gbp_ba_detach_comm(gbp_handle h);
+int gbp_ba_comm_info(gbp_handle h, int32_t out[2] /* rank, nranks (0, 1 without a communicator) */);
+/* For host-driven schedules and phase timing: after gbp_ba_sweep_local(... | GBP_STAGE_BELIEFS | GBP_STAGE_DEFER_LANDMARKS),
+ * all-gather the chunk sums and finalise the keyframe beliefs on the handle's stream (gbp_ba_landmark_update does the rest). */
+int gbp_ba_exchange(gbp_handle h);
+
+/* n x synchronous_iteration(robustify, local_relin) (gbp/gbp.py:86-92; the loop of ba.py:84-105 without the client's
+ * per-iteration reads): sweep + belief update (with a communicator: + the keyframe exchange), replayed from a CUDA graph. */
 int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin);
-/* FactorGraph.update_all_beliefs alone (gbp/gbp.py:56-58), single GPU. */
+/* FactorGraph.update_all_beliefs alone (gbp/gbp.py:56-58). */
 int gbp_ba_update_beliefs(gbp_handle h);
 
 /* BAFactorGraph.are (gbp/gbp_ba.py:61-69), FactorGraph.energy (gbp/gbp.py:36-44) and the count of
@@ -230,8 +258,9 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
 int gbp_ba_synchronize(gbp_handle h);
 /* Engine tuning knobs (no reference counterpart; measurement scripts): GBP_TUNE_PREFETCH_TILES = L2 prefetch distance of the
  * streaming build in tiles (0 = off; the automatic choice is ~38 k edges ahead); GBP_TUNE_BELIEF_LANES = lanes per landmark in the
- * belief kernel (1, 8, 32; 0 = chosen by the number of landmarks). */
-enum { GBP_TUNE_PREFETCH_TILES = 3, GBP_TUNE_BELIEF_LANES = 5 };
+ * belief kernel (1, 8, 32; 0 = chosen by the number of landmarks); GBP_TUNE_LMK_STORE_POLICY = L2 eviction policy of the sweep's
+ * factor->landmark message stores, which the belief kernel reads back (0 default, 1 evict_last, 2 evict_first). */
+enum { GBP_TUNE_PREFETCH_TILES = 3, GBP_TUNE_BELIEF_LANES = 5, GBP_TUNE_LMK_STORE_POLICY = 6 };
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value);
 /* Timing helper for benchmarks: runs n_iters iterations bracketed by CUDA events on the handle's
  * stream; *ms_total = elapsed device time, *ms_msg_kernel = summed time of the message kernel alone

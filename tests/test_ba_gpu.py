@@ -80,6 +80,31 @@ def test_reprojection_model_matches_oracle():
     assert np.max(np.abs(J - Jo) / (1 + np.abs(Jo))) < 1e-11
 
 
+def test_reprojection_special_branches_on_the_device():
+    """The branches of so3exp / dR_wx_dw that random inputs never reach, evaluated by the DEVICE code (sincos / rsqrt intrinsics, not
+    the host build's libm): |w| < 3 eps -> R = I (utils/lie_algebra.py:34-35); w = 0 -> the w-block of the Jacobian is NaN exactly
+    like the reference (utils/derivatives.py:43-44: 0 / 0); a rotation just above the threshold takes the Rodrigues branch."""
+    from gbp_b200.engine import reprojection_eval
+    from oracle import gbp_oracle as O
+    x = np.zeros((4, 9))
+    x[:, 2] = 3.0
+    x[:, 6:9] = [0.3, -0.2, 1.0]
+    x[1, 3:6] = [1e-16, 0.0, 0.0]                 # |w| < 3 eps, w != 0: identity rotation, finite Jacobian
+    x[2, 3:6] = [1e-9, -2e-9, 5e-10]              # just above the threshold
+    x[3, 3:6] = [6.0e-16, 2.0e-16, 1.0e-16]       # |w| = 6.4e-16 < 6.66e-16: still the identity branch
+    K4 = np.array([517.306408, 516.469215, 318.64304, 255.313989])
+    h, J = reprojection_eval(x, K4)
+    Ko = O.K_matrix(K4)
+    with np.errstate(all="ignore"):
+        ho, Jo = O.meas_fn(x, Ko), O.jac_fn(x, Ko)
+    assert np.array_equal(np.isnan(J), np.isnan(Jo)) and np.isnan(J[0, :, 3:6]).all() and not np.isnan(J[1:]).any()
+    assert not np.isnan(h).any()
+    assert np.max(np.abs(h - ho) / (1 + np.abs(ho))) < 1e-12
+    ok = ~np.isnan(Jo)
+    assert np.max(np.abs(J[ok] - Jo[ok]) / (1 + np.abs(Jo[ok]))) < 1e-9
+    assert np.array_equal(h[0], h[1]) and np.array_equal(h[0], h[3])          # all three used R = I
+
+
 def test_known_answer_factor0():
     """SURVEY section 8(c) known answers for factor 0 of fr1desk_vsmall through the proxy objects."""
     from gbp_b200.ba import create_ba_graph
@@ -286,6 +311,35 @@ def test_proxy_api_surface():
     assert r.shape == (2,) and abs(np.linalg.norm(r) - graph.factors[0].reprojection_err()) < 1e-12
     assert abs(np.mean([np.linalg.norm(x) for x in np.array(graph.compute_residuals()).reshape(-1, 2)]) - graph.are()) < 1e-9
     graph.close()
+
+
+def test_belief_write_keeps_the_mean_consistent():
+    """A client that rebinds node.belief.eta / .lam (or node.mu) on a live graph: every consumer of the reference takes the mean
+    as Lambda^-1 eta (gbp/gbp.py:71, 192-193), so after the write-through the device row's mean is Lambda^-1 eta of what was
+    written; an assigned mu alone stands only while Lambda is still zero (the initial state)."""
+    from gbp_b200.ba import create_ba_graph
+    from gbp_b200 import _lib as L
+    G = load_golden("fr1desk_vsmall")
+    g = create_ba_graph(golden_problem(G), golden_configs(G))
+    n0 = g.cam_nodes[0]
+    n0.mu = n0.mu + 0.25                                   # initial state: Lambda = 0, the written mean is kept
+    g._flush()
+    assert np.allclose(g._eng.read(L.F_CAM_MU)[0], G["in_cam0"][0] + 0.25, rtol=0, atol=0)
+    g.reset()
+    g.generate_priors_var(50.0); g.update_all_beliefs()
+    g.iterate(3, robustify=True, local_relin=True)
+    n = g.cam_nodes[1]
+    eta, lam, mu = n.belief.eta, n.belief.lam, n.mu
+    n.belief.eta = 2.0 * eta
+    n.mu = mu + 5.0                                        # no effect where Lambda > 0: the sweep would never see it in the reference either
+    g._flush()
+    row = g._eng.read(L.F_CAM_BELIEF)[1]
+    want = np.linalg.solve(lam, 2.0 * eta)
+    assert np.allclose(row[27:], want, rtol=1e-10, atol=1e-12) and np.allclose(row[:6], 2.0 * eta, rtol=0, atol=0)
+    assert np.array_equal(g._eng.read(L.F_CAM_MU)[1], row[27:])
+    other = g._eng.read(L.F_CAM_BELIEF)[2]
+    assert np.allclose(other[27:], np.linalg.solve(g.cam_nodes[2].belief.lam, other[:6]), rtol=1e-10, atol=1e-12)
+    g.close()
 
 
 def test_edge_cases():

@@ -40,6 +40,8 @@ def _worker(rank, world, port, out_dir):
     trace.append(pg.metrics())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), means=pg.get_means(), trace=np.array(trace), n_iterations=pg.n_iterations)
     pg.close()
+    from gbp_b200.dist import shutdown
+    shutdown()
     dist.destroy_process_group()
 
 
@@ -90,3 +92,52 @@ def test_two_gpu_partition_matches_single_gpu(tmp_path):
         g.synchronous_iteration(robustify=True, local_relin=True)
     assert np.array_equal(g.get_means(), r0["means"])
     g.close()
+
+
+def test_native_exchange_world_of_one_matches_plain_engine(built_library):
+    """The library's own NCCL path (gbp_ba_attach_comm) on ONE GPU: a communicator of one rank runs the complete distributed
+    iteration (side stream, chunk sums, ncclAllGather, keyframe update, cross-rank metric sums) and must reproduce the plain
+    engine bit for bit.  Runs on the driver's single-GPU box, where the 2-GPU test is skipped."""
+    from gbp_b200.engine import BAEngine, Communicator
+    from gbp_b200.synthetic import make_synthetic
+    from gbp_b200 import _lib as L
+    prob = make_synthetic(30, 3000, 8, seed=7)
+    comm = Communicator(Communicator.unique_id(), 0, 1, device=0)
+    args = (prob.cam_id, prob.lmk_id, prob.z, prob.cam_means, prob.lmk_means, prob.K4, CFG)
+    chunks = (4, 0, 4, 0, prob.n_points)
+    out = []
+    for with_comm in (False, True):
+        e = BAEngine(*args, chunks=chunks)
+        if with_comm:
+            e.attach_comm(comm)
+            assert e.comm_info() == (0, 1)
+            with pytest.raises(L.GbpError):
+                comm.destroy()                                 # refused while a graph is attached
+        e.generate_priors(50.0)
+        e.update_beliefs()
+        e.iterate(3, robustify=True, local_relin=True)
+        e.fill_iters(1)
+        e.iterate(17, robustify=True, local_relin=True)        # REPS-of-8 graphs and single-iteration graphs
+        m = e.metrics()
+        out.append((e.read(L.F_CAM_MU).copy(), e.read(L.F_LMK_MU).copy(), m, e.read(L.F_CAM_BELIEF).copy()))
+        if with_comm:
+            n0 = e.launch_count()
+            e.iterate(1, robustify=True, local_relin=True)
+            assert e.launch_count() - n0 == 4                  # sweep, keyframe chunk sums, landmark beliefs, keyframe update
+            e.detach_comm()
+            assert e.comm_info() == (0, 1)
+            e.iterate(1, robustify=True, local_relin=True)     # back to the plain two-kernel iteration
+        e.close()
+    comm.destroy()
+    (c0, l0, m0, b0), (c1, l1, m1, b1) = out
+    assert np.array_equal(c0, c1) and np.array_equal(l0, l1) and np.array_equal(b0, b1)
+    assert m0 == m1
+
+
+def test_communicator_argument_checks(built_library):
+    from gbp_b200.engine import Communicator
+    from gbp_b200._lib import GbpError
+    with pytest.raises(ValueError):
+        Communicator(b"short", 0, 1)
+    with pytest.raises(GbpError):
+        Communicator(b"\0" * 128, 2, 2)        # rank out of range: refused before NCCL is asked
