@@ -23,7 +23,7 @@ COMM_ID_BYTES = 128
 ST_ROBUSTIFY, ST_RELIN, ST_MESSAGES, ST_BELIEFS, ST_LOCAL_DAMPING, ST_DEFER_LANDMARKS = 1, 2, 4, 8, 16, 32
 
 LOSS_CODES = {None: 0, "huber": 1, "constant": 2}
-TUNE_PREFETCH_TILES, TUNE_BELIEF_LANES, TUNE_LMK_STORE_POLICY = 3, 5, 6
+TUNE_PREFETCH_TILES, TUNE_BELIEF_LANES = 3, 5
 
 # field -> (index kind, dtype, row width)
 FIELD_SHAPES = {

@@ -99,7 +99,6 @@ struct gbp_ba_graph {
     long long launches = 0;
     int K_chunks = 1;         // landmark chunks of the keyframe-side sums (gbp_config)
     int belief_lanes = 0;     // lanes per landmark in belief_kernel: 0 = by graph size (GBP_TUNE_BELIEF_LANES)
-    int lmk_policy = 0;       // L2 policy of the factor->landmark message stores (GBP_TUNE_LMK_STORE_POLICY)
 
     // host copies (factor order)
     std::vector<int> h_slot_of_factor, h_file_of_factor, h_adj;
@@ -108,7 +107,7 @@ struct gbp_ba_graph {
     DevBuf<Tile> tiles;
     DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
-    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu;
+    DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu, cam_chol;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
 
     std::map<int, cudaGraphExec_t> graphs;  // key: stages
@@ -265,12 +264,12 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     SweepParams p{};
     p.tiles = g->tiles.p; p.lmk_idx = g->lmk_idx.p; p.z = g->z.p; p.linpoint = g->linpoint.p;
     p.msg_cam = g->msg_cam.p; p.msg_lmk = g->msg_lmk.p; p.iters = g->iters.p; p.flags = g->flags.p;
-    p.sigma2a = g->sigma2a.p; p.cam_belief = g->cam_belief.p; p.lmk_belief = g->lmk_belief.p;
+    p.sigma2a = g->sigma2a.p; p.cam_belief = g->cam_belief.p; p.cam_chol = g->cam_chol.p; p.lmk_belief = g->lmk_belief.p;
     p.tile_partial = g->tile_partial.p; p.K = g->K;
     p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std;
     p.eta_damping = g->cfg.eta_damping; p.beta = g->cfg.beta; p.nstds = g->cfg.Nstds;
     p.num_undamped = g->cfg.num_undamped_iters; p.min_linear = g->cfg.min_linear_iters;
-    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles; p.pf_dist = g->pf_dist; p.lmk_policy = g->lmk_policy;
+    p.loss = g->cfg.loss; p.stages = stages; p.n_tiles = g->n_tiles; p.pf_dist = g->pf_dist;
     return p;
 }
 
@@ -312,7 +311,7 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, cudaStream_t str
     p.msg_lmk = g->msg_lmk.p; p.lmk_prior = g->lmk_prior.p; p.lmk_belief = g->lmk_belief.p;
     p.lmk_ptr = g->lmk_ptr.p; p.lmk_slots = g->lmk_slots.p; p.tile_partial = g->tile_partial.p;
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
-    p.cam_belief = g->cam_belief.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
+    p.cam_belief = g->cam_belief.p; p.cam_chol = g->cam_chol.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.cam_chunk_ptr = g->cam_chunk_ptr.p; p.K = g->K_chunks;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
     // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds; from ~50 k
@@ -612,12 +611,22 @@ int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_boun
     return GBP_OK;
 }
 
+// Automatic number of landmark chunks: the largest power of two <= 8 that leaves a chunk at least 125000 landmarks.  Every chunk
+// boundary ends the (chunk, keyframe) runs of edges and with them a partly filled tile per keyframe, so small chunks cost padding
+// (125 k landmarks / 1000 keyframes / 10 observations cut into 8 chunks: 22 % padding slots, sweep 6 % slower); 8 chunks of the
+// 1 M-landmark graph cost 1.2 %.
+int auto_chunks(long long L) {
+    int K = 1;
+    while (K < 8 && L / (2 * K) >= 125000) K *= 2;
+    return K;
+}
+
 // The chunking of a graph: local landmark boundaries of its chunks from the configuration (see gbp_config), 0 = automatic.
 int chunk_bounds_of(const gbp_config* cfg, int L, std::vector<long long>* cb) {
     int K = cfg ? cfg->lmk_chunks : 0;
     long long first = 0, total = 0, lmk_first = 0, lmk_total = L;
     if (K <= 0) {
-        K = L >= 65536 ? 8 : 1;
+        K = auto_chunks(L);
         total = K;
     } else {
         first = cfg->lmk_chunk_first; total = cfg->lmk_chunks_total; lmk_first = cfg->lmk_first; lmk_total = cfg->lmk_total;
@@ -735,6 +744,7 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         ALLOC(msg_cam, S * (size_t)g->cam_w); ALLOC(msg_lmk, S * LMK_M);
         ALLOC(cam_prior, (size_t)C * CAM_M); ALLOC(lmk_prior, (size_t)L * LMK_M); ALLOC(cam_partial, (size_t)g->K_chunks * C * CAM_M);
         ALLOC(tile_partial, tiles.size() * CAM_M); ALLOC(edge_max, S); ALLOC(tile_max, tiles.size()); ALLOC(cam_max, (size_t)C);
+        ALLOC(cam_chol, (size_t)C * CHOL6);
         zero_end = A.used;
         ALLOC(iters, S); ALLOC(flags, S); ALLOC(linpoint, S * 9); ALLOC(sigma2a, S);
         ALLOC(tile_metric, tiles.size() * 3);
@@ -965,7 +975,7 @@ int gbp_ba_cam_update(gbp_handle h, const double* partials_dev, int nranks) {
     const double* src = partials_dev ? partials_dev : h->cam_partial.p;
     if (!partials_dev) nranks = h->K_chunks;
     if (nranks < 1) return fail(GBP_ERR_INVALID, "the number of partial sums must be >= 1");
-    cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p, h->cam_mu.p);
+    cam_update_kernel<<<(h->C + 3) / 4, 128, 0, h->stream>>>(src, nranks, h->C, h->cam_prior.p, h->cam_belief.p, h->cam_mu.p, h->cam_chol.p);
     h->launches++;
     CU(cudaGetLastError());
     return GBP_OK;
@@ -1161,8 +1171,8 @@ int gbp_ba_write(gbp_handle h, int field, const void* host_src, size_t bytes) {
     if (!host_src) return fail(GBP_ERR_INVALID, "null source");
     if (fi.indexed != 2) {
         CU(cudaMemcpyAsync(field_dev_ptr(h, field), host_src, need, cudaMemcpyHostToDevice, h->stream));
-        if (field == GBP_F_CAM_BELIEF) refresh_mu_kernel<6><<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_belief.p, h->C, CAM_B, h->cam_mu.p);
-        if (field == GBP_F_LMK_BELIEF) refresh_mu_kernel<3><<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->lmk_belief.p, h->L, LMK_B, h->lmk_mu.p);
+        if (field == GBP_F_CAM_BELIEF) refresh_mu_kernel<6><<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->cam_belief.p, h->C, CAM_B, h->cam_mu.p, h->cam_chol.p);
+        if (field == GBP_F_LMK_BELIEF) refresh_mu_kernel<3><<<(h->L + 127) / 128, 128, 0, h->stream>>>(h->lmk_belief.p, h->L, LMK_B, h->lmk_mu.p, nullptr);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(h->stream));
         if (field == GBP_F_CAM_PRIOR || field == GBP_F_LMK_PRIOR) h->priors_set = true;
@@ -1232,15 +1242,6 @@ int gbp_ba_tune(gbp_handle h, int knob, int64_t value) {
             if (value != 0 && value != 1 && value != 8 && value != 32) return fail(GBP_ERR_INVALID, "lanes per landmark: 0 (automatic), 1, 8 or 32");
             CU(cudaStreamSynchronize(h->stream));
             h->belief_lanes = (int)value;
-            for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
-            h->graphs.clear();
-            for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);
-            h->snap_graphs.clear();
-            return GBP_OK;
-        case GBP_TUNE_LMK_STORE_POLICY:
-            if (value < 0 || value > 2) return fail(GBP_ERR_INVALID, "store policy: 0 (default), 1 (evict_last) or 2 (evict_first)");
-            CU(cudaStreamSynchronize(h->stream));
-            h->lmk_policy = (int)value;
             for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
             h->graphs.clear();
             for (auto& kv : h->snap_graphs) cudaGraphExecDestroy(kv.second);

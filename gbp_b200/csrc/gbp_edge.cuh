@@ -34,6 +34,7 @@ struct SweepParams {
     int* flags;
     double* sigma2a;
     const double* cam_belief;
+    const double* cam_chol;    // [C][CHOL6] packed Cholesky factor of every keyframe belief's precision (written with the belief)
     const double* lmk_belief;
     double* tile_partial;
     Intrinsics K;
@@ -41,7 +42,6 @@ struct SweepParams {
     int num_undamped, min_linear, loss, stages;
     int n_tiles;
     int pf_dist;   // > 0: a CTA also prefetches the streams of tile (its tile + pf_dist) into L2 (early-issue kernels)
-    int lmk_policy;   // L2 policy of the factor->landmark message stores (re-read by belief_kernel): 0 default, 1 evict_last, 2 evict_first
 };
 
 // per-edge register inputs fetched straight from global memory
@@ -56,10 +56,12 @@ struct EdgeRegs {
 // (read, then overwritten in place with the new messages / linearisation point); s_cb is the
 // keyframe belief row shared by the whole tile.  Returns true when the edge relinearised.
 // FACTORED: my_mc is an 18-double row eta[6] | W[2][6] (Lambda = W^T W) and my_full receives the message in the full
-// 27-double form eta | Lambda for the keyframe-side sum (whenever the stages include the belief sums).
+// 27-double form eta | Lambda for the keyframe-side sum (whenever the stages include the belief sums); s_ch is the packed
+// Cholesky factor of the keyframe belief's precision (cholesky6_packed, shared by the tile): the message to the landmark
+// down-dates it by the old rank-2 message instead of factoring the cavity per edge (message_downdated).
 template <bool ROBUST, bool FACTORED = false>
 GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const double* s_cb, double* my_lp, double* my_mc,
-                       double* my_ml, double* my_full = nullptr) {
+                       double* my_ml, double* my_full = nullptr, const double* s_ch = nullptr) {
     const double* z = r.z;
     const double* bl = r.bl;
     int it = r.it, fl = r.fl;
@@ -135,22 +137,20 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
             if (it == p.num_undamped) fl |= 1;
             damping = (fl & 1) ? p.eta_damping : 0.0;
         }
-        // message to the landmark: marginalise the keyframe (6x6 Cholesky)
+        // message to the landmark: marginalise the keyframe (6x6 Cholesky; FACTORED: down-date of the tile's shared factor)
         double nl_eta[3], nl_lam[6];
         {
-            double P[21], ev[6];
+            double ev[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) ev[k] = s_cb[k] - my_mc[k];
             if (FACTORED) {
-                double old_lam[21];
-                expand_factored6(my_mc + 6, old_lam);
-#pragma unroll
-                for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - old_lam[k];
+                message_downdated<3>(J + 6, J, b, var, s_ch, my_mc + 6, ev, damping, my_ml, nl_eta, nl_lam);
             } else {
+                double P[21];
 #pragma unroll
                 for (int k = 0; k < 21; ++k) P[k] = s_cb[6 + k] - my_mc[6 + k];
+                message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
             }
-            message<3, 6>(J + 6, J, b, var, P, ev, damping, my_ml, nl_eta, nl_lam);
         }
         // message to the keyframe: marginalise the landmark (3x3 Cholesky); written in place
         {

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
     double* s_red = s_cb + 34;           // [T/32][27]
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + (T / 32) * CAM_M);
     double* s_full = s_red + (T / 32) * CAM_M + 2;   // [T][27] full-form messages of the tile (STREAM only)
+    double* s_ch = s_full + T * CAM_M;               // [21] packed Cholesky factor of the keyframe belief's precision (STREAM only)
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
         }
     }
     for (int i = tid; i < CAM_B; i += T) s_cb[i] = p.cam_belief[(long long)tl.cam * CAM_B + i];   // T may be 32 < 33
+    if (STREAM && tid >= T - CHOL6) s_ch[tid - (T - CHOL6)] = p.cam_chol[(long long)tl.cam * CHOL6 + tid - (T - CHOL6)];   // the other end of the CTA
     if (!STREAM && tid < n) load_edge_regs(p, base + tid, r);
     __syncthreads();          // s_cb visible
     mbar_wait(bar, 0);        // bulk loads landed
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
     bool relin = false;
     if (tid < n)
         relin = edge_sweep<ROBUST, STREAM>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
-                                           STREAM ? s_full + tid * CAM_M : nullptr);
+                                           STREAM ? s_full + tid * CAM_M : nullptr, STREAM ? s_ch : nullptr);
     fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
 
@@ -259,8 +261,7 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
         const uint64_t pol = policy_evict_first();
         if (p.stages & ST_MESSAGES) {
             bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
-            if (p.lmk_policy == 0) bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
-            else bulk_s2g_hint(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8, p.lmk_policy == 1 ? policy_evict_last() : pol);
+            bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
         }
         if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
         bulk_commit();
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
 
 template <int T, bool STREAM>
 constexpr size_t sweep_smem_bytes() {
-    return sizeof(double) * (size_t)(T * ((STREAM ? CAM_MF + CAM_M : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */);
+    return sizeof(double) * (size_t)(T * ((STREAM ? CAM_MF + CAM_M : CAM_M) + LMK_M + 9) + 34 + (T / 32) * CAM_M + 2 /* mbarrier */ +
+                                     (STREAM ? CHOL6 + 1 : 0));
 }
 
 // ----------------------------------------------------------------------------------------
@@ -293,6 +295,7 @@ struct BeliefParams {
     const int* cam_tiles;    // [n_tiles]
     const double* cam_prior;
     double* cam_belief;
+    double* cam_chol;        // [C][CHOL6] packed Cholesky factor of the keyframe precisions (read by the streaming sweep)
     double* cam_partial;     // [K][C][27]  sums of the factor->keyframe messages per landmark chunk
     const int* cam_chunk_ptr;   // [C][K + 1] positions in cam_tiles where the chunks of a keyframe start
     int K;                   // landmark chunks
@@ -302,20 +305,38 @@ struct BeliefParams {
     int parts;               // bit0: keyframe CTAs, bit1: landmark CTAs (multi-GPU runs them as two launches)
 };
 
-__device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out) {
-    // lanes 0..26 hold eta[6] | Lambda[21]; gather to lane 0, solve, write the 33-double row
+__device__ __forceinline__ void cam_finalise_row(const double acc /*lane k<27*/, int lane, double* row, double* mu_out, double* chol_out) {
+    // lanes 0..26 hold eta[6] | Lambda[21]; gather to lane 0, factor, solve, write the 33-double row and the packed factor
     double v[CAM_M];
 #pragma unroll
     for (int k = 0; k < CAM_M; ++k) v[k] = __shfl_sync(0xffffffffu, acc, k);
     if (lane < CAM_M) row[lane] = acc;
     if (lane == 0) {
-        double mu[6];
-        spd_solve<6>(v + 6, v, mu);
+        double L[36], invd[6], y[6], mu[6];
+        cholesky<6>(v + 6, L, invd);
+        forward<6>(L, invd, v, y);
+#pragma unroll
+        for (int ii = 0; ii < 6; ++ii) {       // back substitution, as in spd_solve
+            const int i = 5 - ii;
+            double t = y[i];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (k > i) t -= L[k * 6 + i] * mu[k];
+            mu[i] = t * invd[i];
+        }
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             row[27 + k] = mu[k];
             mu_out[k] = mu[k];
         }
+        int q = 0;
+#pragma unroll
+        for (int i = 1; i < 6; ++i)
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (k < i) chol_out[q++] = L[i * 6 + k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) chol_out[15 + i] = invd[i];
     }
 }
 
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
             }
             acc += p.cam_prior[(long long)c * CAM_M + lane];
         }
-        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6);
+        if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6, p.cam_chol + (long long)c * CHOL6);
         return;
     }
     // ---- landmarks: LMK_LANES lanes gather one landmark's message rows in parallel, then a
@@ -425,7 +446,8 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
 // keyframe beliefs from the gathered chunk sums (multi-GPU): chunk sums in chunk order, then the prior -- the association of belief_kernel
 __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restrict__ partials, int nranks, int C,
                                                          const double* __restrict__ cam_prior,
-                                                         double* __restrict__ cam_belief, double* __restrict__ cam_mu) {
+                                                         double* __restrict__ cam_belief, double* __restrict__ cam_mu,
+                                                         double* __restrict__ cam_chol) {
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -437,7 +459,7 @@ __global__ void __launch_bounds__(128) cam_update_kernel(const double* __restric
         }
         acc += cam_prior[(long long)c * CAM_M + lane];
     }
-    cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B, cam_mu + (long long)c * 6);
+    cam_finalise_row(acc, lane, cam_belief + (long long)c * CAM_B, cam_mu + (long long)c * 6, cam_chol + (long long)c * CHOL6);
 }
 
 
@@ -663,7 +685,7 @@ __global__ void init_belief_kernel(const double* mu0, int V, int N, int brow, do
 // consumer of the reference computes it (gbp/gbp.py:71, 192-193) -- a written `mu` only stands where Lambda is still zero (the
 // initial state); then the compact means are refreshed
 template <int N>
-__global__ void refresh_mu_kernel(double* belief, int V, int brow, double* mu_compact) {
+__global__ void refresh_mu_kernel(double* belief, int V, int brow, double* mu_compact, double* chol /* N == 6: [V][CHOL6], else nullptr */) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     double* row = belief + (long long)v * brow;
@@ -678,6 +700,7 @@ __global__ void refresh_mu_kernel(double* belief, int V, int brow, double* mu_co
         for (int k = 0; k < N; ++k) ok = ok && (mu[k] == mu[k]);      // not positive definite after all: keep the written mean
         if (ok)
             for (int k = 0; k < N; ++k) row[brow - N + k] = mu[k];
+        if (N == 6 && chol) cholesky6_packed(lam, chol + (long long)v * CHOL6);
     }
     for (int k = 0; k < N; ++k) mu_compact[(long long)v * N + k] = row[brow - N + k];
 }

@@ -14,9 +14,11 @@ does: cut the problem (`local_problem`), choose the layout from the GLOBAL sizes
 id from rank 0 to the other ranks over the caller's `torch.distributed` group (any backend), and concatenate the means.
 
 Bit-identical across the NUMBER of GPUs as well: the engine forms the keyframe-side sums per landmark CHUNK (gbp_config:
-8 chunks of consecutive landmarks from 65536 landmarks on) and adds the chunk sums in chunk order; a rank holds whole chunks of
+up to 8 chunks of at least 125 000 consecutive landmarks) and adds the chunk sums in chunk order; a rank holds whole chunks of
 that global chunking and lays out exactly the tiles the single-GPU plan has for them (tile size, landmark blocks and kernel
-build are chosen from the GLOBAL sizes).  So 1, 2, 4 and 8 GPUs run the same floating-point operations in the same order.
+build are chosen from the GLOBAL sizes).  So 1, 2, 4 and 8 GPUs run the same floating-point operations in the same order
+(whenever the automatic chunk count is a multiple of the number of GPUs -- 8 chunks from 1 M landmarks on; otherwise the run uses
+one chunk per rank and equals the single-GPU engine created with that chunking, `chunks=(world, 0, world, 0, n_landmarks)`).
 
 (A collective-free exchange -- every rank storing its partial sums into the other ranks' buffers over NVLink through CUDA IPC
 mappings, per-CTA flags -- was built and run on 2 and 8 GPUs in round 2: same bits, same speed as the all-gather within 1 %
@@ -50,7 +52,9 @@ def global_layout(prob: BALProblem, world: int):
     F, Lm = prob.n_edges, prob.n_points
     T = 64 if F >= 64 * 148 * 6 else 32
     lblock = max(Lm, 1) if Lm * 96 <= (24 << 20) else 262144
-    k_auto = 8 if Lm >= 65536 else 1
+    k_auto = 1
+    while k_auto < 8 and Lm // (2 * k_auto) >= 125000:      # auto_chunks() of gbp_ba.cu
+        k_auto *= 2
     k_total = k_auto if k_auto % world == 0 else world
     variant = 2 if (F // T > 8192 and T <= 64) else 1
     lanes = 1 if Lm >= 49152 else (8 if Lm > 8192 else 32)         # belief_kernel: the lane count fixes the landmark summation order

@@ -69,8 +69,8 @@ typedef struct gbp_config {
      * rank whole chunks of the SAME global chunking, so the keyframe beliefs -- and with them the whole trajectory -- are
      * bit-identical for 1, 2, 4 and 8 GPUs.  Chunk k of lmk_chunks_total covers the global landmarks
      * [lmk_total * k / lmk_chunks_total, lmk_total * (k + 1) / lmk_chunks_total); this graph holds lmk_chunks of them starting at
-     * chunk lmk_chunk_first, its landmark 0 being global landmark lmk_first.  lmk_chunks = 0: automatic (the whole graph: 8 chunks
-     * from 65536 landmarks on, else 1). */
+     * chunk lmk_chunk_first, its landmark 0 being global landmark lmk_first.  lmk_chunks = 0: automatic (the whole graph in the
+     * largest power of two <= 8 of chunks that leaves a chunk at least 125000 landmarks: 8 from 1 M landmarks on). */
     int32_t lmk_chunks, lmk_chunk_first, lmk_chunks_total, reserved0;
     int64_t lmk_first, lmk_total;
 } gbp_config;
@@ -258,9 +258,8 @@ int gbp_ba_set_params(gbp_handle h, double eta_damping, double beta, int32_t num
 int gbp_ba_synchronize(gbp_handle h);
 /* Engine tuning knobs (no reference counterpart; measurement scripts): GBP_TUNE_PREFETCH_TILES = L2 prefetch distance of the
  * streaming build in tiles (0 = off; the automatic choice is ~38 k edges ahead); GBP_TUNE_BELIEF_LANES = lanes per landmark in the
- * belief kernel (1, 8, 32; 0 = chosen by the number of landmarks); GBP_TUNE_LMK_STORE_POLICY = L2 eviction policy of the sweep's
- * factor->landmark message stores, which the belief kernel reads back (0 default, 1 evict_last, 2 evict_first). */
-enum { GBP_TUNE_PREFETCH_TILES = 3, GBP_TUNE_BELIEF_LANES = 5, GBP_TUNE_LMK_STORE_POLICY = 6 };
+ * belief kernel (1, 8, 32; 0 = chosen by the number of landmarks). */
+enum { GBP_TUNE_PREFETCH_TILES = 3, GBP_TUNE_BELIEF_LANES = 5 };
 int gbp_ba_tune(gbp_handle h, int knob, int64_t value);
 /* Timing helper for benchmarks: runs n_iters iterations bracketed by CUDA events on the handle's
  * stream; *ms_total = elapsed device time, *ms_msg_kernel = summed time of the message kernel alone

@@ -75,15 +75,14 @@ def fr1desk(reps):
             emit({"graph": "fr1desk", "run": tag, "error": f"{type(ex).__name__}: {ex}", "trace": traceback.format_exc()[-600:]})
 
 
-def synthetic(cams, lmks, tiles, blocks, pfs, iters, lanes=(0,), policies=(0,)):
+def synthetic(cams, lmks, tiles, blocks, pfs, iters, lanes=(0,)):
     prob = make_synthetic(cams, lmks, 10, seed=0)
     base = None
     for T in tiles:
         for blk in blocks:
           for ln in lanes:
-           for pol in policies:
             for pf in pfs:
-                tag = f"T{T}_blk{blk}_pf{pf}_lanes{ln}_pol{pol}"
+                tag = f"T{T}_blk{blk}_pf{pf}_lanes{ln}"
                 try:
                     g = create_ba_graph(prob, CFG, tile_edges=T, lmk_block=blk)
                     e = g._eng
@@ -91,8 +90,6 @@ def synthetic(cams, lmks, tiles, blocks, pfs, iters, lanes=(0,), policies=(0,)):
                         e.tune(L.TUNE_BELIEF_LANES, ln)
                     if pf >= 0:
                         e.tune(L.TUNE_PREFETCH_TILES, pf)
-                    if pol:
-                        e.tune(L.TUNE_LMK_STORE_POLICY, pol)
                     g.generate_priors_var(50.0)
                     g.update_all_beliefs()
                     e.iterate(5, True, True)
@@ -124,13 +121,16 @@ def main():
     ap.add_argument("--pf", default="-1", help="L2 prefetch distances in tiles (-1 = automatic)")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--lanes", default="0", help="lanes per landmark of the belief kernel (1, 8, 32; 0 = automatic)")
-    ap.add_argument("--policy", default="0", help="L2 policy of the factor->landmark message stores (0 default, 1 evict_last, 2 evict_first)")
+    ap.add_argument("--lib", default="", help="load this build of libgbp_b200.so instead of the in-tree one (A/B of two builds on one box)")
     a = ap.parse_args()
+    if a.lib:
+        L.LIB_PATH = os.path.abspath(a.lib)
+        emit({"lib": L.LIB_PATH})
     if a.fr1desk:
         fr1desk(a.reps)
     if a.synthetic:
         synthetic(a.cams, a.lmks, [int(x) for x in a.tiles.split(",")], [int(x) for x in a.blocks.split(",")],
-                  [int(x) for x in a.pf.split(",")], a.iters, [int(x) for x in a.lanes.split(",")], [int(x) for x in a.policy.split(",")])
+                  [int(x) for x in a.pf.split(",")], a.iters, [int(x) for x in a.lanes.split(",")])
 
 
 if __name__ == "__main__":

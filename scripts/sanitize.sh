@@ -13,7 +13,7 @@ from gbp_b200.synthetic import make_synthetic
 from gbp_b200.ba import create_ba_graph
 cfg = dict(gauss_noise_std=2, loss="huber", Nstds=3.0, beta=0.01, num_undamped_iters=6, min_linear_iters=8, eta_damping=0.4)
 prob = make_synthetic(40, 70000, 9, seed=1)          # 630 k factors -> 9.9 k tiles of 64: streaming build, 8 landmark chunks
-g = create_ba_graph(prob, cfg)
+g = create_ba_graph(prob, cfg, chunks=(8, 0, 8, 0, prob.n_points))
 e = g._eng
 print("tiles", e.n_tiles, "x", e.tile_edges, "build", e.sweep_variant, "chunks", e.lmk_chunks, "prefetch", e.prefetch_tiles)
 assert e.sweep_variant == 2 and e.lmk_chunks == 8

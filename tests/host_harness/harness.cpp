@@ -34,6 +34,22 @@ void hh_messages(const double* x0, const double* z, long n, const double* K4, do
     }
 }
 
+// The landmark message two ways: message<3, 6> on the explicit cavity P = Lam_b - W0^T W0 (factored per edge), and
+// message_downdated<3> on the shared factor of Lam_b.  lam_b packed 21, W0 2x6, e 6, J 18, b 2 per case.
+void hh_message_downdated(const double* J, const double* b, const double* var, const double* lam_b, const double* W0, const double* e,
+                          const double* damping, const double* old_eta, long n, double* out_explicit, double* out_downdated) {
+    for (long i = 0; i < n; ++i) {
+        const double *Ji = J + 18 * i, *Wi = W0 + 12 * i;
+        double old_lam[21], P[21], ch[CHOL6];
+        expand_factored6(Wi, old_lam);
+        for (int k = 0; k < 21; ++k) P[k] = lam_b[21 * i + k] - old_lam[k];
+        message<3, 6>(Ji + 6, Ji, b + 2 * i, var[i], P, e + 6 * i, damping[i], old_eta + 3 * i, out_explicit + 9 * i, out_explicit + 9 * i + 3);
+        cholesky6_packed(lam_b + 21 * i, ch);
+        message_downdated<3>(Ji + 6, Ji, b + 2 * i, var[i], ch, Wi, e + 6 * i, damping[i], old_eta + 3 * i, out_downdated + 9 * i,
+                             out_downdated + 9 * i + 3);
+    }
+}
+
 void hh_solve6(const double* P, const double* r, long n, double* x) {
     for (long i = 0; i < n; ++i) spd_solve<6>(P + 21 * i, r + 6 * i, x + 6 * i);
 }
@@ -88,8 +104,10 @@ struct HostSweep {
             double *lp = &linpoint[9 * e], *ml = &msg_lmk[(size_t)LMK_M * e];
             if (factored) {
                 double *mc = &msg_cam[(size_t)CAM_MF * e], *full = &msg_full[(size_t)CAM_M * e];
-                if (robust) edge_sweep<true, true>(p, e, r, cb, lp, mc, ml, full);
-                else edge_sweep<false, true>(p, e, r, cb, lp, mc, ml, full);
+                double ch[CHOL6];   // the kernels get it once per keyframe from the belief update
+                cholesky6_packed(cb + 6, ch);
+                if (robust) edge_sweep<true, true>(p, e, r, cb, lp, mc, ml, full, ch);
+                else edge_sweep<false, true>(p, e, r, cb, lp, mc, ml, full, ch);
             } else {
                 double* mc = &msg_cam[(size_t)CAM_M * e];
                 if (robust) edge_sweep<true>(p, e, r, cb, lp, mc, ml);

@@ -33,6 +33,7 @@ def hh():
     vp = C.c_void_p
     lib.hh_linearise.argtypes = [vp, C.c_long, vp, vp, vp]
     lib.hh_messages.argtypes = [vp, vp, C.c_long, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp]
+    lib.hh_message_downdated.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_long, vp, vp]
     lib.hh_solve6.argtypes = lib.hh_solve3.argtypes = [vp, vp, C.c_long, vp]
     lib.hh_robust_variance.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
     lib.hh_robust_variance.restype = C.c_double
@@ -181,6 +182,41 @@ def test_low_rank_messages_equal_the_schur_complement_form(hh):
     num = np.abs(_sym(out_l[:, 3:], 3) - o.msg_lmk_lam).reshape(F, -1).max(axis=1)
     den = np.abs(o.msg_lmk_lam).reshape(F, -1).max(axis=1)
     assert np.max(num / den) < 1e-7
+
+
+def test_downdated_landmark_message_equals_the_explicit_cavity(hh):
+    """message_downdated (shared Cholesky factor of the keyframe belief, rank-2 down-date by the old message: what the streaming
+    kernel runs) against message<3, 6> on the explicitly formed cavity, for keyframes of many edges (the old message is a small
+    share of the belief), of few edges (a large share) and with a zero old message (first sweep)."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    J = rng.normal(size=(n, 18)) * rng.uniform(0.1, 200.0, size=(n, 1))
+    b = rng.normal(size=(n, 2)) * 50
+    var = rng.uniform(0.5, 40.0, size=n)
+    W0 = rng.normal(size=(n, 2, 6)) * rng.uniform(0.05, 30.0, size=(n, 1, 1))
+    W0[:100] = 0.0                                                   # zero old message
+    share = np.concatenate([np.full(100, 1.0), 10.0 ** rng.uniform(-5, -0.3, size=n - 100)])     # information of the others / old message
+    lam_b = np.zeros((n, 6, 6))
+    for i in range(n):
+        R = rng.normal(size=(6, 6))
+        others = R @ R.T + 6 * np.eye(6)
+        old = W0[i].T @ W0[i]
+        scale = (np.trace(old) / np.trace(others)) / share[i] if np.trace(old) > 0 else 1.0
+        lam_b[i] = old + others * max(scale, 1e-12) if np.trace(old) > 0 else others
+    iu = np.triu_indices(6)
+    lam_p = np.ascontiguousarray(lam_b[:, iu[0], iu[1]])
+    e = rng.normal(size=(n, 6)) * 100
+    damping = np.where(rng.uniform(size=n) < 0.5, 0.4, 0.0)
+    old_eta = rng.normal(size=(n, 3))
+    out_a, out_b = np.zeros((n, 9)), np.zeros((n, 9))
+    hh.hh_message_downdated(_p(J), _p(b), _p(var), _p(lam_p), _p(np.ascontiguousarray(W0.reshape(n, 12))), _p(e), _p(damping), _p(old_eta),
+                            n, _p(out_a), _p(out_b))
+    assert np.isfinite(out_a).all() and np.isfinite(out_b).all()
+    # cond(M) ~ 1 / (1 - share of this edge): both forms lose those digits; compare at that scale
+    tol = 1e-11 / np.minimum(share, 1.0)
+    err = np.max(np.abs(out_a - out_b), axis=1) / np.max(np.abs(out_a), axis=1)
+    assert np.all(err < tol), (float(err.max()), int(np.argmax(err / tol)))
+    assert err[:100].max() < 1e-13 and np.median(err) < 1e-13
 
 
 @pytest.mark.parametrize("n", [3, 6])

@@ -121,14 +121,18 @@ def test_plan_shuffled_file_order_and_isolated_variables(built_library):
 
 
 def test_plan_large_graph_auto_tiling(built_library):
-    """Automatic choices: 64-edge tiles from 56832 factors on; 8 landmark chunks from 65536 landmarks on (the keyframe-side sums
-    are associated chunk by chunk, identically on 1, 2, 4 and 8 GPUs); landmark blocks of at most 262144 inside a chunk."""
+    """Automatic choices: 64-edge tiles from 56832 factors on; landmark chunks of at least 125000 landmarks, a power of two <= 8
+    of them (the keyframe-side sums are associated chunk by chunk, identically on 1, 2, 4 and 8 GPUs); landmark blocks of at
+    most 262144 inside a chunk."""
     from gbp_b200.synthetic import make_synthetic
     prob = make_synthetic(50, 300_000, 4, seed=2)
     plan = _plan(prob.cam_id, prob.lmk_id, prob.n_keyframes, prob.n_points)
     assert plan["T"] == 64
-    _check(plan, np.asarray(prob.cam_id), np.asarray(prob.lmk_id), prob.n_keyframes, prob.n_points, 262144, K=8)
-    assert plan["n_chunks"] == 8 and len(np.unique(plan["tile_chunk"])) == 8
+    _check(plan, np.asarray(prob.cam_id), np.asarray(prob.lmk_id), prob.n_keyframes, prob.n_points, 262144, K=2)
+    assert plan["n_chunks"] == 2 and len(np.unique(plan["tile_chunk"])) == 2
+    for n_lmk, want in ((100, 1), (124_999, 1), (249_999, 1), (250_000, 2), (999_999, 4), (1_000_000, 8), (5_000_000, 8)):
+        tiny = _plan(np.zeros(1, np.int32), np.zeros(1, np.int32), 1, n_lmk)
+        assert tiny["n_chunks"] == want, (n_lmk, tiny["n_chunks"], want)
     waste = plan["n_slots"] / len(prob.cam_id) - 1.0
     assert waste < 0.05                                                 # padding slots: < 5 % on this graph
 
