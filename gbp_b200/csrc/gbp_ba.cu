@@ -83,7 +83,6 @@ struct DevBuf {
 struct gbp_ba_graph {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
     gbp_config cfg{};
     Intrinsics K{};
     int C = 0, L = 0;
@@ -186,6 +185,27 @@ long long g_cache_stats[4] = {0, 0, 0, 0};   // creates, arena reuses, graph reu
 
 ShapeKey make_key(const gbp_ba_graph* g);
 
+// ONE library stream per device (plus one high-priority stream for the keyframe branch of multi-GPU iterations), created on first
+// use and kept for the life of the process: handles created with stream = NULL share it.  Measured on fr1desk (scripts/
+// diag_second_graph*.py): as soon as CUDA graphs have been launched on a SECOND stream of the process, every graph replay -- on
+// both streams, for the rest of the process -- runs ~5 % slower (8.68 -> 9.1 us per iteration); a second graph on the SAME stream
+// costs nothing.  So a stream per handle (the obvious design) is the slow one.
+cudaStream_t library_stream(int device, bool high_priority) {
+    static std::mutex mu;
+    static std::map<int, cudaStream_t> streams[2];
+    std::lock_guard<std::mutex> lk(mu);
+    auto& m = streams[high_priority ? 1 : 0];
+    auto it = m.find(device);
+    if (it != m.end()) return it->second;
+    cudaStream_t s = nullptr;
+    int lo = 0, hi = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    if (high_priority && cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : 0) != cudaSuccess) return nullptr;
+    m[device] = s;
+    return s;
+}
+
 // Best shell for a new graph: the one of the same shape (its graphs stay valid), else the smallest arena that fits.
 bool cache_take(const ShapeKey& key, int device, size_t arena_need, Shell* out) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -240,7 +260,6 @@ gbp_ba_graph::~gbp_ba_graph() {
     } else {
         sh.free_all();
     }
-    if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
 namespace {
@@ -679,9 +698,8 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
     if (stream) {
         g->stream = reinterpret_cast<cudaStream_t>(stream);
     } else {
-        cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { return fail(GBP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-        g->own_stream = true;
+        g->stream = library_stream(device, /*high_priority=*/false);
+        if (!g->stream) return fail(GBP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
     }
 
     // ---------------- host graph compiler ----------------
@@ -986,14 +1004,18 @@ int gbp_ba_iterate(gbp_handle h, int n_iters, int robustify, int local_relin) {
     if (n_iters < 0) return fail(GBP_ERR_INVALID, "n_iters < 0");
     if (!h->priors_set) return fail(GBP_ERR_STATE, "priors not set: call gbp_ba_generate_priors / gbp_ba_set_priors first");
     const int st = iteration_stages(robustify, local_relin);
-    constexpr int REPS = 8;
     const int per_iter = launches_per_iteration(h);
     int left = n_iters;
-    if (left >= REPS && h->n_tiles <= 8192) {   // small graphs only: there the launch gaps are a visible share of an iteration
-        cudaGraphExec_t exec8;
-        int rc = get_graph(h, st, &exec8, REPS);
-        if (rc != GBP_OK) return rc;
-        for (; left >= REPS; left -= REPS) CU(cudaGraphLaunch(exec8, h->stream));
+    if (h->n_tiles <= 8192) {
+        // small graphs only: there the gaps between graph launches are a visible share of a ~9 us iteration, so long runs replay
+        // graphs of 32 and 8 iterations (fr1desk: 10.3 us per iteration with one iteration per launch, 9.1 with 8, 8.x with 32)
+        for (int reps : {32, 8}) {
+            if (left < reps) continue;
+            cudaGraphExec_t exec;
+            int rc = get_graph(h, st, &exec, reps);
+            if (rc != GBP_OK) return rc;
+            for (; left >= reps; left -= reps) CU(cudaGraphLaunch(exec, h->stream));
+        }
     }
     if (left > 0) {
         cudaGraphExec_t exec;

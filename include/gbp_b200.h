@@ -13,7 +13,7 @@
  *     returns a thread-local description.  CUDA errors are captured, never abort().
  *   - all host pointers are caller-owned, copied before return, never retained.
  *   - all floating point is IEEE float64, indices are int32.
- *   - one handle = one CUDA device + one stream; calls on a handle are not re-entrant.
+ *   - one handle = one CUDA device + one stream (its own or the library's); calls on a handle are not re-entrant.
  *   - "factor order" is the reference's: camera-major, file order within a camera
  *     (gbp/gbp_ba.py:128-143), i.e. a stable sort of the measurement list by camera id.
  *   - symmetric matrices cross the ABI PACKED, upper triangle row-major:
@@ -119,7 +119,9 @@ int gbp_device_count(void);
 /* create_ba_graph (gbp/gbp_ba.py:97-150) after read_balfile: builds the device-resident graph from
  * the measurement list (file order), linearises every factor at the initial means
  * (gbp/gbp_ba.py:136-137 -> gbp/gbp.py:267-294), zero messages, iters_since_relin = 1, damping 0.
- * `stream` is a cudaStream_t (NULL = the handle creates its own).  n_cam_total/n_lmk are the sizes
+ * `stream` is a cudaStream_t (NULL = the library's stream of that device, shared by all handles created with NULL: CUDA graphs
+ * replayed on more than one stream of a process were measured ~5 % slower, on every stream.  Handles that share the library's
+ * stream must not be driven from different threads at the same time -- give each its own stream for that).  n_cam_total/n_lmk are the sizes
  * of cam_mu0 / lmk_mu0; every camera id < C, landmark id < L. */
 int gbp_ba_create(const gbp_config* cfg, int32_t C, int32_t L, int64_t F,
                   const int32_t* cam_id, const int32_t* lmk_id, const double* z /* F x 2 */,

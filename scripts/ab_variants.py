@@ -43,15 +43,15 @@ def solve(e):
     e.iterate(192, True, True)
 
 
-def fr1desk(reps):
+def fr1desk(reps, variants=(0,)):
     G = np.load(os.path.join(ROOT, "tests", "golden", "fr1desk.npz"))
     prob = balio.BALProblem(G["in_cam_id"], G["in_lmk_id"], G["in_z"], G["in_cam0"], G["in_lmk0"], G["in_K"])
     mu_ref = np.concatenate([G["s199_cam_mu"], G["s199_lmk_mu"]])
     base = None
-    runs = [("run1", 0), ("run2", 0)]
+    runs = [(f"kv{v}_run{r}", v) for r in (1, 2) for v in variants]
     for tag, w in runs:
         try:
-            g = create_ba_graph(prob, CFG)
+            g = create_ba_graph(prob, CFG, kernel_variant=w)
             e = g._eng
             times = []
             for it in range(reps + 2):
@@ -121,13 +121,14 @@ def main():
     ap.add_argument("--pf", default="-1", help="L2 prefetch distances in tiles (-1 = automatic)")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--lanes", default="0", help="lanes per landmark of the belief kernel (1, 8, 32; 0 = automatic)")
+    ap.add_argument("--kv", default="0", help="fr1desk: kernel_variant values to run (0 automatic, 1 full rows, 2 streaming build)")
     ap.add_argument("--lib", default="", help="load this build of libgbp_b200.so instead of the in-tree one (A/B of two builds on one box)")
     a = ap.parse_args()
     if a.lib:
         L.LIB_PATH = os.path.abspath(a.lib)
         emit({"lib": L.LIB_PATH})
     if a.fr1desk:
-        fr1desk(a.reps)
+        fr1desk(a.reps, [int(x) for x in a.kv.split(",")])
     if a.synthetic:
         synthetic(a.cams, a.lmks, [int(x) for x in a.tiles.split(",")], [int(x) for x in a.blocks.split(",")],
                   [int(x) for x in a.pf.split(",")], a.iters, [int(x) for x in a.lanes.split(",")])
