@@ -56,3 +56,40 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f"{f} references the oracle"
+
+
+def test_cpp_shard_client_builds_against_the_header_and_fails_loudly_without_a_gpu(built_library, tmp_path):
+    """examples/shard_client.cpp needs nothing but include/gbp_b200.h and the library (no NCCL header, no torch); on a host
+    without a device it reports the library's error instead of computing anything on the CPU."""
+    import subprocess
+    from gbp_b200 import _lib, balio
+    exe = str(tmp_path / "shard_client")
+    lib_dir = os.path.dirname(built_library)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", os.path.join(ROOT, "examples", "shard_client.cpp"),
+                    "-I" + os.path.join(ROOT, "include"), "-L" + lib_dir, "-lgbp_b200", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    G = np.load(os.path.join(ROOT, "tests", "golden", "fr1desk_vsmall.npz"))
+    prob = balio.BALProblem(G["in_cam_id"], G["in_lmk_id"], G["in_z"], G["in_cam0"], G["in_lmk0"], G["in_K"])
+    bal = str(tmp_path / "p.txt")
+    balio.write_bal(bal, prob)
+    res = subprocess.run([exe, "--rank", "0", "--nranks", "1", "--id-file", str(tmp_path / "id"), "--bal", bal, "--iters", "2"],
+                         capture_output=True, text=True, timeout=120)
+    if _lib.load().gbp_device_count() > 0:
+        assert res.returncode == 0 and "after   2 ARE" in res.stdout, res.stderr
+    else:
+        assert res.returncode == 1 and "no CPU fallback" in res.stderr, (res.returncode, res.stderr)
+    bad = subprocess.run([exe, "--rank", "3", "--nranks", "2", "--bal", bal], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 2 and "usage" in bad.stderr
+
+
+def test_comm_api_without_a_device(built_library):
+    """The multi-GPU entry points check their arguments before touching NCCL or a device."""
+    from gbp_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.gbp_comm_create(None, 0, 1, 0, ctypes.byref(h)) == 1                          # GBP_ERR_INVALID: null id
+    assert lib.gbp_comm_create(ctypes.c_char_p(b"\0" * 128), 2, 2, 0, ctypes.byref(h)) == 1   # rank out of range
+    assert lib.gbp_comm_destroy(None) == 0
+    assert lib.gbp_ba_attach_comm(None, None) != 0 and lib.gbp_ba_exchange(None) != 0
+    assert _lib.comm_version() >= 20000                                                      # an NCCL 2.x is loadable in this image
+    if lib.gbp_device_count() == 0:
+        assert lib.gbp_comm_create(ctypes.c_char_p(b"\0" * 128), 0, 1, 0, ctypes.byref(h)) == 3   # GBP_ERR_NO_DEVICE
