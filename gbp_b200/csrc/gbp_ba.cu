@@ -104,7 +104,7 @@ struct gbp_ba_graph {
 
     // device state
     DevBuf<Tile> tiles;
-    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr;
+    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr, tile_pos, lmk_slot32;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu, cam_chol;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
@@ -284,7 +284,7 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     p.tiles = g->tiles.p; p.lmk_idx = g->lmk_idx.p; p.z = g->z.p; p.linpoint = g->linpoint.p;
     p.msg_cam = g->msg_cam.p; p.msg_lmk = g->msg_lmk.p; p.iters = g->iters.p; p.flags = g->flags.p;
     p.sigma2a = g->sigma2a.p; p.cam_belief = g->cam_belief.p; p.cam_chol = g->cam_chol.p; p.lmk_belief = g->lmk_belief.p;
-    p.tile_partial = g->tile_partial.p; p.K = g->K;
+    p.tile_partial = g->tile_partial.p; p.tile_pos = g->tile_pos.p; p.K = g->K;
     p.var0 = g->cfg.gauss_noise_std * g->cfg.gauss_noise_std;
     p.eta_damping = g->cfg.eta_damping; p.beta = g->cfg.beta; p.nstds = g->cfg.Nstds;
     p.num_undamped = g->cfg.num_undamped_iters; p.min_linear = g->cfg.min_linear_iters;
@@ -332,6 +332,7 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, cudaStream_t str
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_chol = g->cam_chol.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.cam_chunk_ptr = g->cam_chunk_ptr.p; p.K = g->K_chunks;
+    p.lmk_slot32 = g->lmk_slot32.n ? g->lmk_slot32.p : nullptr;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
     // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds; from ~50 k
     // landmarks on one thread per landmark wins (125 k landmarks / 1.25 M factors, the per-rank share at 8 GPUs: 45 vs 57 us)
@@ -493,6 +494,8 @@ struct GraphPlan {
     std::vector<int> lmk_idx;                                  // [slots] landmark of the edge in that slot (0 in padding)
     std::vector<double> z;                                     // [slots][2] (only when measurements were given)
     std::vector<int> lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
+    std::vector<int> tile_pos;                                 // [tiles] position of a tile in cam_tiles (the order its partial sums are stored in)
+    std::vector<int> lmk_slot32;                               // [L][32] the first 32 slots of every landmark, -1 padded (graphs of <= 8192 landmarks)
     int n_chunks = 1;
     std::vector<int> tile_chunk;                               // [tiles] landmark chunk of every tile
     std::vector<int> cam_chunk_ptr;                            // [C][chunks + 1] positions in cam_tiles where a keyframe's chunks start
@@ -614,6 +617,17 @@ int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_boun
     {
         std::vector<int> pos(plan->cam_tile_ptr.begin(), plan->cam_tile_ptr.end() - 1);
         for (size_t t = 0; t < tiles.size(); ++t) plan->cam_tiles[(size_t)pos[tiles[t].cam]++] = (int)t;
+    }
+    plan->tile_pos.assign(tiles.size(), 0);
+    for (size_t q = 0; q < tiles.size(); ++q) plan->tile_pos[(size_t)plan->cam_tiles[q]] = (int)q;
+    // small graphs are latency-bound: the belief kernel reads a landmark's first 32 slots from a dense table (one dependent load
+    // less than lmk_ptr -> lmk_slots -> rows)
+    plan->lmk_slot32.clear();
+    if (L > 0 && L <= 8192) {
+        plan->lmk_slot32.assign((size_t)L * 32, -1);
+        for (int l = 0; l < L; ++l)
+            for (int q = plan->lmk_ptr[l]; q < plan->lmk_ptr[l + 1] && q < plan->lmk_ptr[l] + 32; ++q)
+                plan->lmk_slot32[(size_t)l * 32 + (q - plan->lmk_ptr[l])] = plan->lmk_slots[(size_t)q];
     }
     // a keyframe's tiles are listed in tile order = chunk-major: where its chunks start
     plan->cam_chunk_ptr.assign((size_t)C * (K + 1), 0);
@@ -756,6 +770,7 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(z, S * 2); ALLOC(slot_of_factor, (size_t)F);
         ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F); ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
         ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3); ALLOC(cam_chunk_ptr, plan.cam_chunk_ptr.size());
+        ALLOC(tile_pos, plan.tile_pos.size()); ALLOC(lmk_slot32, plan.lmk_slot32.size());
         g->upload_bytes = A.used - g->upload_off;
         // zero region: everything gbp_ba_reset clears, contiguous -> ONE memset
         zero_off = A.used;
@@ -792,7 +807,8 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
             {plan.lmk_ptr.data(), plan.lmk_ptr.size() * 4, g->lmk_ptr.p}, {plan.lmk_slots.data(), plan.lmk_slots.size() * 4, g->lmk_slots.p},
             {plan.cam_tile_ptr.data(), plan.cam_tile_ptr.size() * 4, g->cam_tile_ptr.p}, {plan.cam_tiles.data(), plan.cam_tiles.size() * 4, g->cam_tiles.p},
             {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p},
-            {plan.cam_chunk_ptr.data(), plan.cam_chunk_ptr.size() * 4, g->cam_chunk_ptr.p}};
+            {plan.cam_chunk_ptr.data(), plan.cam_chunk_ptr.size() * 4, g->cam_chunk_ptr.p},
+            {plan.tile_pos.data(), plan.tile_pos.size() * 4, g->tile_pos.p}, {plan.lmk_slot32.data(), plan.lmk_slot32.size() * 4, g->lmk_slot32.p}};
         constexpr size_t STAGE_MAX = size_t(32) << 20;   // larger graphs upload table by table (a page-locked block that size costs more than it saves)
         if (g->upload_bytes <= STAGE_MAX) {
             if (g->stage_bytes < g->upload_bytes) {

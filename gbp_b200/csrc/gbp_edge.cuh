@@ -37,6 +37,7 @@ struct SweepParams {
     const double* cam_chol;    // [C][CHOL6] packed Cholesky factor of every keyframe belief's precision (written with the belief)
     const double* lmk_belief;
     double* tile_partial;
+    const int* tile_pos;       // [tiles] where a tile's partial sum goes: its position in the keyframe-major tile list
     Intrinsics K;
     double var0, eta_damping, beta, nstds;
     int num_undamped, min_linear, loss, stages;
