@@ -292,6 +292,14 @@ SweepParams sweep_params(gbp_ba_graph* g, int stages) {
     return p;
 }
 
+template <int T, bool ROBUST, bool STREAM>
+void launch_sweep_k(gbp_ba_graph* g, const SweepParams& p, size_t smem) {
+    // the complete synchronous iteration gets the build with compile-time stages (a non-robust graph ignores the robustify stage)
+    const int st = p.stages & ST_FULL;
+    if ((st | (ROBUST ? 0 : ST_ROBUSTIFY)) == ST_FULL) sweep_kernel<T, ROBUST, STREAM, ST_FULL><<<g->n_tiles, T, smem, g->stream>>>(p);
+    else sweep_kernel<T, ROBUST, STREAM, 0><<<g->n_tiles, T, smem, g->stream>>>(p);
+}
+
 template <int T>
 int launch_sweep_t(gbp_ba_graph* g, int stages) {
     const SweepParams p = sweep_params(g, stages);
@@ -301,13 +309,13 @@ int launch_sweep_t(gbp_ba_graph* g, int stages) {
         constexpr int TP = T <= 64 ? T : 64;      // T <= 64 checked at creation
         constexpr size_t smem = sweep_smem_bytes<TP, true>();
         static_assert(smem <= 48 * 1024, "factored sweep tile must fit the default dynamic shared memory limit");
-        if (g->robust) sweep_kernel<TP, true, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
-        else sweep_kernel<TP, false, true><<<g->n_tiles, TP, smem, g->stream>>>(p);
+        if (g->robust) launch_sweep_k<TP, true, true>(g, p, smem);
+        else launch_sweep_k<TP, false, true>(g, p, smem);
     } else {
         constexpr size_t smem = sweep_smem_bytes<T, false>();
         static_assert(smem <= 48 * 1024, "sweep tile must fit the default dynamic shared memory limit");
-        if (g->robust) sweep_kernel<T, true, false><<<g->n_tiles, T, smem, g->stream>>>(p);
-        else sweep_kernel<T, false, false><<<g->n_tiles, T, smem, g->stream>>>(p);
+        if (g->robust) launch_sweep_k<T, true, false>(g, p, smem);
+        else launch_sweep_k<T, false, false>(g, p, smem);
     }
     g->launches++;
     CU(cudaGetLastError());

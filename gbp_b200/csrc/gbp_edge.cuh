@@ -60,9 +60,15 @@ struct EdgeRegs {
 // 27-double form eta | Lambda for the keyframe-side sum (whenever the stages include the belief sums); s_ch is the packed
 // Cholesky factor of the keyframe belief's precision (cholesky6_packed, shared by the tile): the message to the landmark
 // down-dates it by the old rank-2 message instead of factoring the cavity per edge (message_downdated).
-template <bool ROBUST, bool FACTORED = false>
+// STAGES: the stages to run as a compile-time constant (the full synchronous iteration: no stage tests in the instruction
+// stream), or 0 = take them from p.stages.
+// The non-robust path is written without data-dependent branches (the rare relinearisation is a handful of selects and
+// predicated stores): together with the branch-free rsqrt / reciprocal the whole edge is then ONE basic block that ptxas can
+// schedule across -- the two independent messages interleave -- which matters at 1-3 warps per scheduler.
+template <bool ROBUST, bool FACTORED = false, int STAGES = 0>
 GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const double* s_cb, double* my_lp, double* my_mc,
                        double* my_ml, double* my_full = nullptr, const double* s_ch = nullptr) {
+    const int stages = STAGES ? STAGES : p.stages;
     const double* z = r.z;
     const double* bl = r.bl;
     int it = r.it, fl = r.fl;
@@ -72,7 +78,7 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
     for (int k = 0; k < 9; ++k) x0[k] = my_lp[k];
 
     // --- relinearisation test (gbp/gbp.py:72-75): |linpoint - [mu_cam, mu_lmk]| > beta
-    if (p.stages & ST_RELIN) {
+    if (stages & ST_RELIN) {
         double d2 = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -92,7 +98,7 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
     bool lin_done = false;
     if (ROBUST) {
         var = r.var;
-        if (p.stages & ST_ROBUSTIFY) {
+        if (stages & ST_ROBUSTIFY) {
             // robustify_loss uses h at the STORED linearisation point (gbp/gbp.py:309-312)
             double r0, r1;
             if (relin) {
@@ -113,29 +119,43 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
         }
     }
 
-    if (p.stages & ST_RELIN) {
-        if (relin) {   // gbp/gbp.py:76-78
+    if (stages & ST_RELIN) {
+        if (ROBUST) {
+            if (relin) {   // gbp/gbp.py:76-78
 #pragma unroll
-            for (int k = 0; k < 6; ++k) x0[k] = s_cb[27 + k];
+                for (int k = 0; k < 6; ++k) x0[k] = s_cb[27 + k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) x0[6 + k] = bl[9 + k];
+                for (int k = 0; k < 3; ++k) x0[6 + k] = bl[9 + k];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];
-            it = 0;
-            fl &= ~1;
-            lin_done = false;
+                for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];
+                it = 0;
+                fl &= ~1;
+                lin_done = false;
+            } else {
+                it += 1;   // gbp/gbp.py:80
+            }
         } else {
-            it += 1;   // gbp/gbp.py:80
+            // the same, as selects (gbp/gbp.py:76-80)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) x0[k] = relin ? s_cb[27 + k] : x0[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x0[6 + k] = relin ? bl[9 + k] : x0[6 + k];
+            if (relin) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) my_lp[k] = x0[k];      // predicated stores
+            }
+            it = relin ? 0 : it + 1;
+            fl = relin ? (fl & ~1) : fl;
         }
     }
 
-    if (p.stages & ST_MESSAGES) {
+    if (stages & ST_MESSAGES) {
         if (!lin_done) linearise(p.K, x0, J, h0);
         double b[2];
         factor_rhs(J, x0, z, h0, b);
         double damping = p.eta_damping;
-        if (p.stages & ST_LOCAL_DAMPING) {   // gbp/gbp.py:49-52
-            if (it == p.num_undamped) fl |= 1;
+        if (stages & ST_LOCAL_DAMPING) {   // gbp/gbp.py:49-52
+            fl = (it == p.num_undamped) ? (fl | 1) : fl;
             damping = (fl & 1) ? p.eta_damping : 0.0;
         }
         // message to the landmark: marginalise the keyframe (6x6 Cholesky; FACTORED: down-date of the tile's shared factor)
@@ -168,7 +188,7 @@ GBP_HD bool edge_sweep(const SweepParams& p, long long e, EdgeRegs& r, const dou
 #pragma unroll
         for (int k = 0; k < 6; ++k) my_ml[3 + k] = nl_lam[k];
     }
-    if (FACTORED && (p.stages & ST_BELIEFS)) {   // full form of the (new or stored) message for the keyframe-side sum
+    if (FACTORED && (stages & ST_BELIEFS)) {   // full form of the (new or stored) message for the keyframe-side sum
 #pragma unroll
         for (int k = 0; k < 6; ++k) my_full[k] = my_mc[k];
         expand_factored6(my_mc + 6, my_full + 6);

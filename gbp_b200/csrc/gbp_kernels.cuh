@@ -181,9 +181,13 @@ __device__ __forceinline__ void tile_column_sums(const SweepParams& p, int tpos,
 // consumer ring, cooperative LDG staging, 128-register builds, register-level column sums, programmatic
 // dependent launches, a completion-counter one-kernel iteration) are in the git history and profiles/README.md.
 // ----------------------------------------------------------------------------------------
-template <int T, bool ROBUST, bool STREAM>
+// STAGES  the stages of the pass as a compile-time constant (ST_FULL: the complete synchronous iteration, what gbp_ba_iterate
+//         replays; no stage tests in the instruction stream) or 0 = take them from p.stages (staged calls).
+constexpr int ST_FULL = ST_ROBUSTIFY | ST_RELIN | ST_MESSAGES | ST_BELIEFS | ST_LOCAL_DAMPING;
+template <int T, bool ROBUST, bool STREAM, int STAGES = 0>
 __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) {
     constexpr bool EARLY = STREAM;   // the early-issue prologue was re-measured on fr1desk in round 2 (same stream, same box): 8.45 vs 8.45 us
+    const int stages = STAGES ? STAGES : p.stages;
     extern __shared__ __align__(128) double smem[];
     constexpr int CW = STREAM ? CAM_MF : CAM_M;
     double* s_mc = smem;                 // [T][27]  (or [T][18] factored)
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
 
     bool relin = false;
     if (tid < n)
-        relin = edge_sweep<ROBUST, STREAM>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
+        relin = edge_sweep<ROBUST, STREAM, STAGES>(p, base + tid, r, s_cb, s_lp + tid * 9, s_mc + tid * CW, s_ml + tid * LMK_M,
                                            STREAM ? s_full + tid * CAM_M : nullptr, STREAM ? s_ch : nullptr);
     fence_async_smem();       // generic-proxy writes -> visible to the bulk-copy engine
     const int any_relin = __syncthreads_or(relin ? 1 : 0);
@@ -262,14 +266,14 @@ __global__ void __launch_bounds__(T, 384 / T) sweep_kernel(const SweepParams p) 
         // the message rows of the landmark are gathered again by belief_kernel: only the big keyframe rows
         // and the linearisation points are marked evict_first
         const uint64_t pol = policy_evict_first();
-        if (p.stages & ST_MESSAGES) {
+        if (stages & ST_MESSAGES) {
             bulk_s2g_hint(p.msg_cam + base * CW, s_mc, (uint32_t)n_even * CW * 8, pol);
             bulk_s2g(p.msg_lmk + base * LMK_M, s_ml, (uint32_t)n_even * LMK_M * 8);
         }
         if (any_relin) bulk_s2g_hint(p.linpoint + base * 9, s_lp, (uint32_t)n_even * 72, pol);
         bulk_commit();
     }
-    if (p.stages & ST_BELIEFS) tile_column_sums<T>(p, tpos, n, STREAM ? s_full : s_mc, s_red);
+    if (stages & ST_BELIEFS) tile_column_sums<T>(p, tpos, n, STREAM ? s_full : s_mc, s_red);
     if (tid == 0) bulk_wait_read0();   // shared memory must outlive the engine's reads
 }
 
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
         // GPUs: a rank holds whole chunks), then the prior
         double acc = 0.0;
         if (lane < CAM_M) {
+            const double prior = p.cam_prior[(long long)c * CAM_M + lane];   // issued with the first loads, not behind the sums
             for (int k = 0; k < p.K; ++k) {
                 const int t0 = p.cam_chunk_ptr[c * (p.K + 1) + k], t1 = p.cam_chunk_ptr[c * (p.K + 1) + k + 1];
                 double part = 0.0;
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
                 p.cam_partial[((long long)k * p.C + c) * CAM_M + lane] = part;
                 acc = k == 0 ? part : acc + part;
             }
-            acc += p.cam_prior[(long long)c * CAM_M + lane];
+            acc += prior;
         }
         if (p.finalise) cam_finalise_row(acc, lane, p.cam_belief + (long long)c * CAM_B, p.cam_mu + (long long)c * 6, p.cam_chol + (long long)c * CHOL6);
         return;
@@ -400,8 +405,14 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     const int l = ((int)blockIdx.x - cam_blocks) * LMK_PER_CTA + (threadIdx.x / LMK_LANES);
     const bool valid = l < p.L;
     double acc[LMK_M];
+    double prior_k = 0.0;
 #pragma unroll
     for (int k = 0; k < LMK_M; ++k) acc[k] = 0.0;
+    if (LMK_LANES == 32) {
+        // small graphs (latency-bound): the prior row is fetched with the first loads, not behind the gather and the tree.  Lane k
+        // of the landmark's warp loads component k (one register per lane); lane 0 collects them by shuffle after the tree.
+        if (valid && sub < LMK_M) prior_k = p.lmk_prior[(long long)l * LMK_M + sub];
+    }
     if (valid && LMK_LANES == 32 && p.lmk_slot32) {
         // small graphs: the first row of every lane comes from the dense slot table (table -> row: two dependent loads instead of
         // lmk_ptr -> lmk_slots -> row); same rows in the same order as the CSR walk below
@@ -448,9 +459,15 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
     for (int o = LMK_LANES / 2; o > 0; o >>= 1)
 #pragma unroll
         for (int k = 0; k < LMK_M; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (valid && sub == 0) {
+    if (LMK_LANES == 32) {
 #pragma unroll
-        for (int k = 0; k < LMK_M; ++k) acc[k] += p.lmk_prior[(long long)l * LMK_M + k];
+        for (int k = 0; k < LMK_M; ++k) acc[k] += __shfl_sync(0xffffffffu, prior_k, k);   // only lane 0's sum is used
+    }
+    if (valid && sub == 0) {
+        if (LMK_LANES != 32) {
+#pragma unroll
+            for (int k = 0; k < LMK_M; ++k) acc[k] += p.lmk_prior[(long long)l * LMK_M + k];
+        }
         double mu[3];
         spd_solve<3>(acc + 3, acc, mu);
         double2* dst = reinterpret_cast<double2*>(p.lmk_belief + (long long)l * LMK_B);
