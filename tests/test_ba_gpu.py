@@ -451,10 +451,19 @@ def test_unmodified_reference_ba_py(data, fixture, extra):
     tr = _parse_ba_trace(out)
     assert tr.shape == (n_iters, 4) and np.array_equal(tr[:, 0], np.arange(n_iters))
     float_impl = bool(G["float_impl"])
-    tol = 1e-3 if float_impl else 1e-6         # the worse-conditioned float trace: see tests/test_math_host.py
+    # The --float_implementation run (100x weaker priors) is ill-conditioned: its last outer iteration (29) sits on an energy
+    # spike (4.4e7 between neighbours of 1e5) that amplifies rounding differences by ~1e13 -- the g++ / libm build of the SAME
+    # per-edge code is 1.2e-3 (full rows) / 1.6e-4 (factored rows) from the reference there and 3e-5 or better everywhere else
+    # (tests/test_math_host.py), device builds landed between 2e-4 and 1.0e-3 depending on the rounding of sin / cos / rsqrt.
+    # So: per iteration 5e-3 on that trace (1e-6 on the others), and the whole trace in the table norm at 1e-4 like the checkpoints.
+    tol = 5e-3 if float_impl else 1e-6
     ref_are, ref_en = G["are"][:n_iters], G["energy"][:n_iters]
     assert np.all(np.abs(tr[:, 1] - ref_are) <= 0.5e-4 + tol * np.abs(ref_are))      # printed with 4 decimals
     assert np.all(np.abs(tr[:, 2] - ref_en) <= 0.5e-4 + tol * np.abs(ref_en))
+    assert relerr(tr[:, 1], ref_are) < 1e-4 and relerr(tr[:, 2], ref_en) < 1e-4
+    if float_impl:
+        ok = np.abs(tr[:, 2] - ref_en) <= 0.5e-4 + 1e-4 * np.abs(ref_en)
+        assert ok[:-1].all(), np.nonzero(~ok)[0]                                     # everything but the spike at 1e-4
     dn = np.abs(tr[:, 3].astype(int) - G["n_relin"][:n_iters])
     assert dn.max() <= (2 if fixture == "fr1desk" else 0), np.nonzero(dn)[0]
     if float_impl:
