@@ -104,7 +104,7 @@ struct gbp_ba_graph {
 
     // device state
     DevBuf<Tile> tiles;
-    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr, tile_pos, lmk_slot32;
+    DevBuf<int> lmk_idx, iters, flags, slot_of_factor, lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles, cam_chunk_ptr, tile_pos;
     DevBuf<double> z, linpoint, msg_cam, msg_lmk, sigma2a;
     DevBuf<double> cam_belief, lmk_belief, cam_prior, lmk_prior, cam_partial, cam_mu0, lmk_mu0, cam_mu, lmk_mu, cam_chol;
     DevBuf<double> tile_partial, tile_metric, metric_out, edge_max, tile_max, cam_max;
@@ -340,7 +340,6 @@ int launch_belief(gbp_ba_graph* g, int finalise, int parts = 3, cudaStream_t str
     p.cam_tile_ptr = g->cam_tile_ptr.p; p.cam_tiles = g->cam_tiles.p; p.cam_prior = g->cam_prior.p;
     p.cam_belief = g->cam_belief.p; p.cam_chol = g->cam_chol.p; p.cam_partial = g->cam_partial.p; p.cam_mu = g->cam_mu.p; p.lmk_mu = g->lmk_mu.p;
     p.cam_chunk_ptr = g->cam_chunk_ptr.p; p.K = g->K_chunks;
-    p.lmk_slot32 = g->lmk_slot32.n ? g->lmk_slot32.p : nullptr;
     p.L = g->L; p.C = g->C; p.finalise = finalise; p.parts = parts;
     // small graphs are latency-bound: a whole warp per landmark gathers a degree-46 landmark in 2 dependent rounds; from ~50 k
     // landmarks on one thread per landmark wins (125 k landmarks / 1.25 M factors, the per-rank share at 8 GPUs: 45 vs 57 us)
@@ -503,7 +502,6 @@ struct GraphPlan {
     std::vector<double> z;                                     // [slots][2] (only when measurements were given)
     std::vector<int> lmk_ptr, lmk_slots, cam_tile_ptr, cam_tiles;
     std::vector<int> tile_pos;                                 // [tiles] position of a tile in cam_tiles (the order its partial sums are stored in)
-    std::vector<int> lmk_slot32;                               // [L][32] the first 32 slots of every landmark, -1 padded (graphs of <= 8192 landmarks)
     int n_chunks = 1;
     std::vector<int> tile_chunk;                               // [tiles] landmark chunk of every tile
     std::vector<int> cam_chunk_ptr;                            // [C][chunks + 1] positions in cam_tiles where a keyframe's chunks start
@@ -525,63 +523,75 @@ int choose_tiling(int tile_edges, long long lmk_block, int L, int64_t F, int* T_
 // chunk_bounds: [chunks + 1] landmark boundaries of the chunks (0 ... L); a landmark block never straddles a chunk
 int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_bounds, int C, int L, int64_t F, const int32_t* cam_id,
                const int32_t* lmk_id, const double* z, GraphPlan* plan) {
-    for (int64_t f = 0; f < F; ++f) {
-        if (cam_id[f] < 0 || cam_id[f] >= C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)f, cam_id[f]);
-        if (lmk_id[f] < 0 || lmk_id[f] >= L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)f, lmk_id[f]);
-    }
+    // Counting sorts only, one pass per table (13 k edges: ~0.2 ms; 10 M edges: ~0.5 s).  Positions fit int32 (checked below).
+    if (F >= (1LL << 31) / 2) return fail(GBP_ERR_INVALID, "graph too large for int32 slots");
     plan->T = T;
     plan->lblock = lblock;
     const int K = std::max<int>(1, (int)chunk_bounds.size() - 1);
     plan->n_chunks = K;
+    const int Cn = std::max(C, 1);
+    // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130); validation in the counting pass
+    std::vector<int> cam_start((size_t)C + 1, 0);
+    for (int64_t i = 0; i < F; ++i) {
+        const int c = cam_id[i], l = lmk_id[i];
+        if ((unsigned)c >= (unsigned)C) return fail(GBP_ERR_INVALID, "measurement %lld: camera id %d out of range", (long long)i, c);
+        if ((unsigned)l >= (unsigned)L) return fail(GBP_ERR_INVALID, "measurement %lld: landmark id %d out of range", (long long)i, l);
+        cam_start[(size_t)c + 1]++;
+    }
+    for (int c = 0; c < C; ++c) cam_start[c + 1] += cam_start[c];
     // landmark blocks: every chunk is cut into blocks of lblock landmarks; blocks are numbered chunk by chunk
-    std::vector<int> blk_of_lmk((size_t)L, 0), chunk_of_blk;
+    std::vector<int> blk_of_lmk((size_t)L), chunk_of_blk;
     for (int k = 0; k < K; ++k) {
         const long long l0 = chunk_bounds.size() > 1 ? chunk_bounds[k] : 0, l1 = chunk_bounds.size() > 1 ? chunk_bounds[k + 1] : L;
         for (long long b0 = l0; b0 < l1; b0 += lblock) {
-            for (long long l = b0; l < std::min(l1, b0 + lblock); ++l) blk_of_lmk[(size_t)l] = (int)chunk_of_blk.size();
+            const int b = (int)chunk_of_blk.size();
+            std::fill(blk_of_lmk.begin() + b0, blk_of_lmk.begin() + std::min(l1, b0 + lblock), b);
             chunk_of_blk.push_back(k);
         }
     }
     if (chunk_of_blk.empty()) chunk_of_blk.push_back(0);
     const long long nb = (long long)chunk_of_blk.size();
+    const size_t nkeys = (size_t)nb * (size_t)Cn;
+    if (nkeys >= (size_t)1 << 31) return fail(GBP_ERR_INVALID, "too many (landmark block, keyframe) runs");
 
-    // factor order = stable sort of the measurement list by camera (gbp/gbp_ba.py:128-130)
-    std::vector<long long> cam_start((size_t)C + 1, 0);
-    for (int64_t i = 0; i < F; ++i) cam_start[cam_id[i] + 1]++;
-    for (int c = 0; c < C; ++c) cam_start[c + 1] += cam_start[c];
-    plan->file_of_factor.assign((size_t)F, 0);
+    // one scatter pass: factor f of measurement i; its (keyframe, landmark), its run key = block * C + keyframe; run sizes
+    plan->file_of_factor.resize((size_t)F);
+    plan->adj.resize((size_t)F * 2);
+    std::vector<int> key((size_t)F);
+    std::vector<int> run_count(nkeys + 1, 0);
     {
-        std::vector<long long> pos(cam_start.begin(), cam_start.end() - 1);
-        for (int64_t i = 0; i < F; ++i) plan->file_of_factor[(size_t)pos[cam_id[i]]++] = (int)i;
+        int* fof = plan->file_of_factor.data();
+        int* adj = plan->adj.data();
+        std::vector<int> pos(cam_start.begin(), cam_start.end() - 1);
+        for (int64_t i = 0; i < F; ++i) {
+            const int c = cam_id[i], l = lmk_id[i];
+            const int f = pos[c]++;
+            fof[f] = (int)i;
+            adj[2 * (size_t)f] = c;
+            adj[2 * (size_t)f + 1] = l;
+            const int k = blk_of_lmk[(size_t)l] * Cn + c;
+            key[(size_t)f] = k;
+            run_count[(size_t)k]++;
+        }
     }
-    plan->adj.assign((size_t)F * 2, 0);
-    for (int64_t f = 0; f < F; ++f) {
-        const int i = plan->file_of_factor[(size_t)f];
-        plan->adj[2 * f] = cam_id[i];
-        plan->adj[2 * f + 1] = lmk_id[i];
-    }
-    // storage order: (landmark block, camera) runs, factor order inside a run
-    const size_t nkeys = (size_t)nb * (size_t)std::max(C, 1);
-    std::vector<long long> run_start(nkeys + 1, 0);
-    auto key_of = [&](int64_t f) { return (size_t)blk_of_lmk[(size_t)plan->adj[2 * f + 1]] * (size_t)C + (size_t)plan->adj[2 * f]; };
-    for (int64_t f = 0; f < F; ++f) run_start[key_of(f) + 1]++;
-    // tiles per run
+    // storage order: (landmark block, camera) runs, factor order inside a run; tiles per run
     std::vector<Tile>& tiles = plan->tiles;
     tiles.clear();
     plan->tile_chunk.clear();
-    std::vector<long long> run_slot(nkeys, 0);
+    std::vector<int> run_slot(nkeys, 0);
     {
         long long tcount = 0;
         for (size_t k = 0; k < nkeys; ++k) {
-            const long long cnt = run_start[k + 1];
-            run_slot[k] = tcount * T;
-            long long left = cnt;
+            if (tcount * T >= (1LL << 31) - 2 * T) return fail(GBP_ERR_INVALID, "graph too large for int32 slots");
+            run_slot[k] = (int)(tcount * T);
+            int left = run_count[k];
+            const int cam = (int)(k % (size_t)Cn), chunk = chunk_of_blk[k / (size_t)Cn];
             while (left > 0) {
                 Tile t;
-                t.cam = (int)(k % (size_t)std::max(C, 1));
-                t.count = (int)std::min<long long>(left, T);
+                t.cam = cam;
+                t.count = std::min(left, T);
                 tiles.push_back(t);
-                plan->tile_chunk.push_back(chunk_of_blk[k / (size_t)std::max(C, 1)]);
+                plan->tile_chunk.push_back(chunk);
                 left -= t.count;
                 ++tcount;
             }
@@ -589,33 +599,41 @@ int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_boun
     }
     const long long n_slots = plan->n_slots();
     if (n_slots >= (1LL << 31)) return fail(GBP_ERR_INVALID, "graph too large for int32 slots");
-    plan->slot_of_factor.assign((size_t)F, 0);
-    {
-        std::vector<long long> pos(run_slot);
-        for (int64_t f = 0; f < F; ++f) plan->slot_of_factor[(size_t)f] = (int)pos[key_of(f)]++;
-        // runs are contiguous in slots except for the padding of their last tile, which lies at
-        // the END of the run, so consecutive positions are correct.
-    }
-    // slot-ordered inputs
+    // one pass in factor order: the slot of every factor (runs are contiguous in slots except for the padding of their last
+    // tile, which lies at the END of the run, so consecutive positions are correct), the slot-ordered inputs, landmark degrees
+    plan->slot_of_factor.resize((size_t)F);
     plan->lmk_idx.assign((size_t)n_slots, 0);
     plan->z.assign(z ? (size_t)n_slots * 2 : 0, 0.0);
-    for (int64_t f = 0; f < F; ++f) {
-        const size_t s = (size_t)plan->slot_of_factor[(size_t)f];
-        const int i = plan->file_of_factor[(size_t)f];
-        plan->lmk_idx[s] = plan->adj[2 * f + 1];
-        if (z) {
-            plan->z[2 * s] = z[2 * (size_t)i];
-            plan->z[2 * s + 1] = z[2 * (size_t)i + 1];
+    plan->lmk_ptr.assign((size_t)L + 1, 0);
+    {
+        int* sof = plan->slot_of_factor.data();
+        int* lidx = plan->lmk_idx.data();
+        double* zs = plan->z.data();
+        int* lptr = plan->lmk_ptr.data();
+        const int* adj = plan->adj.data();
+        const int* fof = plan->file_of_factor.data();
+        for (int64_t f = 0; f < F; ++f) {
+            const int s = run_slot[(size_t)key[(size_t)f]]++;
+            const int l = adj[2 * (size_t)f + 1];
+            sof[f] = s;
+            lidx[s] = l;
+            lptr[(size_t)l + 1]++;
+            if (z) {
+                const size_t i = (size_t)fof[f];
+                zs[2 * (size_t)s] = z[2 * i];
+                zs[2 * (size_t)s + 1] = z[2 * i + 1];
+            }
         }
     }
     // CSR by landmark over slots (factor order inside a landmark = adj_factors order)
-    plan->lmk_ptr.assign((size_t)L + 1, 0);
-    plan->lmk_slots.assign((size_t)F, 0);
-    for (int64_t f = 0; f < F; ++f) plan->lmk_ptr[(size_t)plan->adj[2 * f + 1] + 1]++;
+    plan->lmk_slots.resize((size_t)F);
     for (int l = 0; l < L; ++l) plan->lmk_ptr[l + 1] += plan->lmk_ptr[l];
     {
         std::vector<int> pos(plan->lmk_ptr.begin(), plan->lmk_ptr.end() - 1);
-        for (int64_t f = 0; f < F; ++f) plan->lmk_slots[(size_t)pos[plan->adj[2 * f + 1]]++] = plan->slot_of_factor[(size_t)f];
+        int* ls = plan->lmk_slots.data();
+        const int* adj = plan->adj.data();
+        const int* sof = plan->slot_of_factor.data();
+        for (int64_t f = 0; f < F; ++f) ls[pos[(size_t)adj[2 * (size_t)f + 1]]++] = sof[f];
     }
     // CSR by camera over tiles
     plan->cam_tile_ptr.assign((size_t)C + 1, 0);
@@ -628,15 +646,6 @@ int plan_graph(int T, long long lblock, const std::vector<long long>& chunk_boun
     }
     plan->tile_pos.assign(tiles.size(), 0);
     for (size_t q = 0; q < tiles.size(); ++q) plan->tile_pos[(size_t)plan->cam_tiles[q]] = (int)q;
-    // small graphs are latency-bound: the belief kernel reads a landmark's first 32 slots from a dense table (one dependent load
-    // less than lmk_ptr -> lmk_slots -> rows)
-    plan->lmk_slot32.clear();
-    if (L > 0 && L <= 8192) {
-        plan->lmk_slot32.assign((size_t)L * 32, -1);
-        for (int l = 0; l < L; ++l)
-            for (int q = plan->lmk_ptr[l]; q < plan->lmk_ptr[l + 1] && q < plan->lmk_ptr[l] + 32; ++q)
-                plan->lmk_slot32[(size_t)l * 32 + (q - plan->lmk_ptr[l])] = plan->lmk_slots[(size_t)q];
-    }
     // a keyframe's tiles are listed in tile order = chunk-major: where its chunks start
     plan->cam_chunk_ptr.assign((size_t)C * (K + 1), 0);
     for (int c = 0; c < C; ++c) {
@@ -778,7 +787,7 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
         ALLOC(tiles, tiles.size()); ALLOC(lmk_idx, S); ALLOC(z, S * 2); ALLOC(slot_of_factor, (size_t)F);
         ALLOC(lmk_ptr, (size_t)L + 1); ALLOC(lmk_slots, (size_t)F); ALLOC(cam_tile_ptr, (size_t)C + 1); ALLOC(cam_tiles, tiles.size());
         ALLOC(cam_mu0, (size_t)C * 6); ALLOC(lmk_mu0, (size_t)L * 3); ALLOC(cam_chunk_ptr, plan.cam_chunk_ptr.size());
-        ALLOC(tile_pos, plan.tile_pos.size()); ALLOC(lmk_slot32, plan.lmk_slot32.size());
+        ALLOC(tile_pos, plan.tile_pos.size());
         g->upload_bytes = A.used - g->upload_off;
         // zero region: everything gbp_ba_reset clears, contiguous -> ONE memset
         zero_off = A.used;
@@ -816,7 +825,7 @@ static int ba_create_impl(const gbp_config* cfg, int32_t C, int32_t L, int64_t F
             {plan.cam_tile_ptr.data(), plan.cam_tile_ptr.size() * 4, g->cam_tile_ptr.p}, {plan.cam_tiles.data(), plan.cam_tiles.size() * 4, g->cam_tiles.p},
             {cam_mu0, (size_t)C * 48, g->cam_mu0.p}, {lmk_mu0, (size_t)L * 24, g->lmk_mu0.p},
             {plan.cam_chunk_ptr.data(), plan.cam_chunk_ptr.size() * 4, g->cam_chunk_ptr.p},
-            {plan.tile_pos.data(), plan.tile_pos.size() * 4, g->tile_pos.p}, {plan.lmk_slot32.data(), plan.lmk_slot32.size() * 4, g->lmk_slot32.p}};
+            {plan.tile_pos.data(), plan.tile_pos.size() * 4, g->tile_pos.p}};
         constexpr size_t STAGE_MAX = size_t(32) << 20;   // larger graphs upload table by table (a page-locked block that size costs more than it saves)
         if (g->upload_bytes <= STAGE_MAX) {
             if (g->stage_bytes < g->upload_bytes) {

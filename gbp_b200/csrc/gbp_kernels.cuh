@@ -305,7 +305,6 @@ struct BeliefParams {
     double* cam_chol;        // [C][CHOL6] packed Cholesky factor of the keyframe precisions (read by the streaming sweep)
     double* cam_partial;     // [K][C][27]  sums of the factor->keyframe messages per landmark chunk
     const int* cam_chunk_ptr;   // [C][K + 1] positions in the keyframe-major tile list where the chunks of a keyframe start
-    const int* lmk_slot32;      // [L][32] first 32 slots of every landmark, -1 padded (small graphs; nullptr otherwise)
     int K;                   // landmark chunks
     double* cam_mu;          // [C][6]  compact copy of the means (snapshot region)
     double* lmk_mu;          // [L][3]
@@ -413,25 +412,7 @@ __global__ void __launch_bounds__(128) belief_kernel(const BeliefParams p) {
         // of the landmark's warp loads component k (one register per lane); lane 0 collects them by shuffle after the tree.
         if (valid && sub < LMK_M) prior_k = p.lmk_prior[(long long)l * LMK_M + sub];
     }
-    if (valid && LMK_LANES == 32 && p.lmk_slot32) {
-        // small graphs: the first row of every lane comes from the dense slot table (table -> row: two dependent loads instead of
-        // lmk_ptr -> lmk_slots -> row); same rows in the same order as the CSR walk below
-        const int slot0 = p.lmk_slot32[(long long)l * 32 + sub];
-        const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
-        if (slot0 >= 0) {
-            double v[9];
-            load_row9(p.msg_lmk + (long long)slot0 * LMK_M, (slot0 & 1) == 0, v);
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += v[k];
-        }
-        for (int q = p0 + 32 + sub; q < p1; q += 32) {     // landmarks of more than 32 edges
-            const int slot = p.lmk_slots[q];
-            double v[9];
-            load_row9(p.msg_lmk + (long long)slot * LMK_M, (slot & 1) == 0, v);
-#pragma unroll
-            for (int k = 0; k < LMK_M; ++k) acc[k] += v[k];
-        }
-    } else if (valid) {
+    if (valid) {
         const int p0 = p.lmk_ptr[l], p1 = p.lmk_ptr[l + 1];
         int q = p0 + sub;
         // four rows in flight per thread (slot loads, then row loads, then the adds in edge order)
