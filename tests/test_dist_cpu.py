@@ -173,3 +173,27 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert np.array_equal(trace[:, 2], r0["trace"][:, 2])
     assert relerr(r0["trace"][:, :2], trace[:, :2]) < 1e-9
     assert relerr(r0["means"], np.concatenate([o.cam_mu.ravel(), o.lmk_mu.ravel()])) < 1e-9
+
+
+def test_global_layout_repeats_the_library_rules(built_library):
+    """dist.global_layout chooses tile size, landmark chunks and kernel build from the GLOBAL sizes so that a rank lays out what the
+    single-GPU plan would; it restates rules that live in gbp_ba.cu (choose_tiling, auto_chunks, the streaming switch).  Check the
+    restatement against the library itself (the host graph compiler needs no GPU) over sizes around every threshold."""
+    from gbp_b200.dist import global_layout
+    from gbp_b200.engine import compile_plan
+    from gbp_b200.balio import BALProblem
+    rng = np.random.default_rng(0)
+    for n_lmk, obs in ((500, 4), (8192, 7), (8193, 7), (49152, 2), (124_999, 1), (250_000, 1), (999_999, 1), (1_000_000, 1)):
+        F = n_lmk * obs
+        cam = rng.integers(0, 8, size=F).astype(np.int32)
+        lmk = np.repeat(np.arange(n_lmk, dtype=np.int32), obs)
+        prob = BALProblem(cam, lmk, np.zeros((F, 2)), np.zeros((8, 6)), np.zeros((n_lmk, 3)), np.array([500.0, 500.0, 320.0, 240.0]))
+        plan = compile_plan(cam, lmk, 8, n_lmk)
+        for world in (1, 2, 4, 8):
+            layout, k_total = global_layout(prob, world)
+            assert layout["tile_edges"] == plan["T"], (n_lmk, obs, world)
+            assert layout["kernel_variant"] == (2 if plan["n_tiles"] > 8192 and plan["T"] <= 64 else 1) or \
+                abs(F // plan["T"] - 8192) < 64            # within padding of the switch the two counts may differ
+            k_auto = plan["n_chunks"]
+            assert k_total == (k_auto if k_auto % world == 0 else world), (n_lmk, world, k_total, k_auto)
+            assert k_total % world == 0
