@@ -14,7 +14,7 @@
 namespace gbp {
 
 constexpr int CAM_B = 33, LMK_B = 12, CAM_M = 27, LMK_M = 9;
-constexpr int CAM_MF = 18;   // keyframe message with factored precision: eta[6] | W[2][6], Lambda = W^T W (kernel_variant 5)
+constexpr int CAM_MF = 18;   // keyframe message with factored precision: eta[6] | W[2][6], Lambda = W^T W (the streaming build, kernel_variant 2)
 
 enum : int { ST_ROBUSTIFY = 1, ST_RELIN = 2, ST_MESSAGES = 4, ST_BELIEFS = 8, ST_LOCAL_DAMPING = 16 };
 

@@ -3,7 +3,7 @@
 // Data layout in HBM (all float64 unless noted; "slot" = position of an edge in the
 // engine's storage order, tile t owns slots [t*T, t*T + count)):
 //   msg_cam   [slots][27]  factor->keyframe message  eta[6] | Lambda packed[21]
-//             [slots][18]  ... or with the rank-2 precision factored: eta[6] | W[2][6], Lambda = W^T W (kernel_variant 5)
+//             [slots][18]  ... or with the rank-2 precision factored: eta[6] | W[2][6], Lambda = W^T W (the streaming build, kernel_variant 2)
 //   msg_lmk   [slots][9]   factor->landmark message  eta[3] | Lambda packed[6]
 //   linpoint  [slots][9]   linearisation point [t, w, y]
 //   z         [slots][2]   measurement

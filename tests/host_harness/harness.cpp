@@ -83,7 +83,7 @@ struct HostSweep {
     long F = 0;
     SweepParams prm{};
     bool robust = false;
-    bool factored = false;   // keyframe messages stored as eta[6] | W[2][6] (kernel_variant 5); msg_full = their 27-wide form
+    bool factored = false;   // keyframe messages stored as eta[6] | W[2][6] (the streaming build); msg_full = their 27-wide form
     std::vector<int> cam, lmk, iters, flags;
     std::vector<double> z, linpoint, msg_cam, msg_lmk, sigma2a, cam_belief, lmk_belief, cam_prior, lmk_prior, msg_full;
 

@@ -102,7 +102,6 @@ def test_synthetic_section_builds_its_json_with_a_stub_engine(monkeypatch):
         def time_iterations(self, k, r, l, per_kernel=False): return 1.2 * k, 1.0 * k
 
     class PG:
-        p2p = False
         n_iterations = 223
         def __init__(self, *a, **kw): self.engine = Eng()
         def generate_priors_var(self, w): pass

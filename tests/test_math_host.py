@@ -288,7 +288,7 @@ def _check_state(s, G, key, tol):
 def test_edge_sweep_trajectory_against_reference_fixture(hh, name, factored):
     """Every checkpoint of the reference run (all loss modes, --float_implementation): beliefs, sampled messages and
     linearisation points, every factor's iters_since_relin and damping flag, the ARE / energy / relinearisation traces.
-    `factored` = the compressed keyframe-message layout (eta | W with Lambda = W^T W, kernel_variant 5)."""
+    `factored` = the compressed keyframe-message layout (eta | W with Lambda = W^T W: the streaming build, kernel_variant 2)."""
     G = load_golden(name)
     cfg = golden_configs(G)
     s = HostSweep(hh, G, cfg, factored)
