@@ -93,3 +93,11 @@ def test_comm_api_without_a_device(built_library):
     assert _lib.comm_version() >= 20000                                                      # an NCCL 2.x is loadable in this image
     if lib.gbp_device_count() == 0:
         assert lib.gbp_comm_create(ctypes.c_char_p(b"\0" * 128), 0, 1, 0, ctypes.byref(h)) == 3   # GBP_ERR_NO_DEVICE
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gbp_b200.h is the boundary a C client binds to: it must compile as C99 on its own (no C++ in the signatures)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gbp_b200.h"\nint main(void) { gbp_config c = {0}; (void)c; return GBP_COMM_ID_BYTES == 128 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-fsyntax-only", str(src)], check=True)
