@@ -16,7 +16,7 @@ lines ``ba.py:79-81,103`` - trimesh/pyglet are not installed) and records
   selected sweeps of ``synchronous_iteration`` (``gbp/gbp.py:86-92``).
 
 Usage:  python tests/golden/make_golden.py [case ...]
-Cases:  vsmall vsmall_huber vsmall_constant vsmall_float fr1desk posegraph synth_small
+Cases:  vsmall vsmall_huber vsmall_constant vsmall_float fr1desk posegraph synth_small fr2robot2 fr1xyz_av fr1desk_small
 """
 import os
 import sys
@@ -180,6 +180,12 @@ def main():
         elif c == "posegraph":
             run_posegraph("posegraph_n50_d3", ["--n_varnodes", "50", "--dim", "3"])
             run_posegraph("posegraph_default", [])
+        elif c == "fr2robot2":      # another sequence: a robot-mounted camera, other intrinsics and motion
+            run_ba("fr2robot2", f"{data}/fr2robot2.txt", 40, {0, 1, 15, 16, 39})
+        elif c == "fr1xyz_av":      # another sequence: pure translation (small rotations)
+            run_ba("fr1xyz_av", f"{data}/fr1xyz_av.txt", 30, {0, 1, 15, 16, 29}, nsample=48)
+        elif c == "fr1desk_small":
+            run_ba("fr1desk_small", f"{data}/fr1desk_small.txt", 40, {0, 1, 15, 16, 39})
         elif c == "synth_small":
             bal = os.path.join(HERE, "synth_small.txt")
             run_ba("synth_small", bal, 30, {0, 1, 15, 16, 29})

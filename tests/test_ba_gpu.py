@@ -132,7 +132,8 @@ def test_known_answer_factor0():
     graph.close()
 
 
-@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float"])
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float",
+                                  "fr2robot2", "fr1desk_small", "fr1xyz_av"])      # the last three: the reference's other data files
 def test_trajectory_against_reference_fixture(name):
     """Every checkpoint of the reference run: beliefs (eta, Lambda, mu), sampled messages and
     linearisation points, and the per-factor relinearisation / damping state, for all loss modes."""
@@ -435,6 +436,7 @@ BA_PY_SHA256 = "ab5d4ac0748cadc8f562fa0e2e3be6a614664166effe66c6721f568e1fe7df86
     ("fr1desk_vsmall.txt", "fr1desk_vsmall_huber", ["--loss", "huber"]),
     ("fr1desk_vsmall.txt", "fr1desk_vsmall_constant", ["--loss", "constant"]),
     ("fr1desk_vsmall.txt", "fr1desk_vsmall_float", ["--float_implementation"]),
+    ("fr2robot2.txt", "fr2robot2", []),
     ("fr1desk.txt", "fr1desk", []),
 ])
 def test_unmodified_reference_ba_py(data, fixture, extra):

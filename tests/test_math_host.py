@@ -284,7 +284,8 @@ def _check_state(s, G, key, tol):
 
 
 @pytest.mark.parametrize("factored", [False, True], ids=["full", "factored"])
-@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float"])
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float",
+                                  "fr2robot2", "fr1desk_small", "fr1xyz_av"])      # the last three: the reference's other data files
 def test_edge_sweep_trajectory_against_reference_fixture(hh, name, factored):
     """Every checkpoint of the reference run (all loss modes, --float_implementation): beliefs, sampled messages and
     linearisation points, every factor's iters_since_relin and damping flag, the ARE / energy / relinearisation traces.

@@ -41,7 +41,8 @@ def test_initial_factors_and_priors():
     assert abs(o.cam_prior_lam[0, 0, 0] - 232.48310953175482) < 1e-9
 
 
-@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float"])
+@pytest.mark.parametrize("name", ["fr1desk_vsmall", "fr1desk_vsmall_huber", "fr1desk_vsmall_constant", "fr1desk_vsmall_float",
+                                  "fr2robot2", "fr1desk_small", "fr1xyz_av"])      # the last three: the reference's other data files
 def test_sweep_trajectory(name):
     """Beliefs, messages, control state and ARE/energy traces over the whole ba.py loop."""
     G = load_golden(name)
